@@ -1,0 +1,437 @@
+"""Acquisition seam of the drop-in boundary: B200 versions of
+bayes_opt.acquisition.{AcquisitionFunction, UpperConfidenceBound, ProbabilityOfImprovement,
+ExpectedImprovement, ConstantLiar} (R/bayes_opt/acquisition.py).
+
+Same class names, constructor arguments, hooks (``_fit_gp``, ``_get_acq``, ``_acq_min``,
+``_random_sample_minimize``, ``_smart_minimize``, ``base_acq``, ``get/set_acquisition_params``),
+decay schedules and exception types as the reference.  What changes is where the arithmetic
+runs: ``_get_acq`` returns a closure that evaluates  -base_acq(mu, sigma) [* p_constraint]  for a
+whole candidate batch in ONE fused sm_100a kernel launch, and ``_random_sample_minimize`` does
+evaluate + argmin + top-k seeds on the device.  Instances duck-type with the reference's
+``BayesianOptimization(acquisition_function=...)``; ``dropin.enable`` swaps
+them into an existing optimizer.
+"""
+from __future__ import annotations
+
+import abc
+import ctypes as C
+import warnings
+from copy import deepcopy
+
+import numpy as np
+from numpy.random import RandomState
+from scipy.optimize import minimize
+from scipy.stats import norm
+
+from . import _lib as B
+from .exception import (
+    ConstraintNotSupportedError,
+    NoValidPointRegisteredError,
+    TargetSpaceEmptyError,
+)
+from .gpr import B200GaussianProcessRegressor
+from .space import ensure_rng
+
+
+def _as_b200_gp(gp):
+    if not isinstance(gp, B200GaussianProcessRegressor):
+        raise TypeError(
+            "the B200 acquisition functions need a B200GaussianProcessRegressor (got "
+            f"{type(gp).__name__}); use bayesianoptimization_b200.enable(optimizer) or construct "
+            "the GP with B200GaussianProcessRegressor - there is no CPU fallback")
+    return gp
+
+
+class FusedAcquisition:
+    """Callable closure over fitted device GPs: x (M,d)|(d,) -> (M,) negated acquisition.
+    Replaces the closure built at R/bayes_opt/acquisition.py:196-219."""
+
+    def __init__(self, kind, gp, constraint=None, kappa=0.0, xi=0.0, y_max=None):
+        gp = _as_b200_gp(gp)
+        gp._ensure_device_fit()
+        self.dim = gp.X_train_.shape[1]
+        self._keep = [gp]
+        spec = B.AcqSpec()
+        spec.kind = kind
+        spec.kappa = float(kappa)
+        spec.xi = float(xi)
+        spec.y_max = float(y_max) if y_max is not None else 0.0
+        spec.gps[0] = gp._handle().ptr.value
+        n = 1
+        if constraint is not None:
+            models = constraint.model
+            if len(models) + 1 > B.MAX_GPS:
+                raise NotImplementedError(f"at most {B.MAX_GPS - 1} constraint GPs are supported")
+            for j, cgp in enumerate(models):
+                cgp = _as_b200_gp(cgp)
+                cgp._ensure_device_fit()
+                self._keep.append(cgp)
+                spec.gps[n] = cgp._handle().ptr.value
+                spec.lb[n] = float(constraint.lb[j])
+                spec.ub[n] = float(constraint.ub[j])
+                n += 1
+        spec.n_gps = n
+        self.spec = spec
+
+    def __call__(self, x):
+        x = B.c_f64(np.asarray(x, dtype=np.float64).reshape(-1, self.dim))
+        out = np.empty(x.shape[0])
+        B.check(B.lib().b200bo_acq_eval(C.byref(self.spec), B.as_dp(x), x.shape[0], B.as_dp(out)))
+        return out
+
+    def argmin_topk(self, x, k):
+        """Evaluate + np.argmin + k smallest (value, index) on the device
+        (R/bayes_opt/acquisition.py:312-317)."""
+        x = B.c_f64(np.asarray(x, dtype=np.float64).reshape(-1, self.dim))
+        best_val = C.c_double()
+        best_idx = C.c_int64()
+        tv = np.empty(max(k, 1))
+        ti = np.empty(max(k, 1), dtype=np.int64)
+        B.check(B.lib().b200bo_acq_argmin_topk(
+            C.byref(self.spec), B.as_dp(x), x.shape[0], int(k), C.byref(best_val), C.byref(best_idx),
+            B.as_dp(tv), ti.ctypes.data_as(C.POINTER(C.c_int64)), None))
+        ti = ti[:k]
+        return best_idx.value, best_val.value, ti[ti >= 0]
+
+
+class AcquisitionFunction(abc.ABC):
+    """Mirror of bayes_opt.acquisition.AcquisitionFunction (R/bayes_opt/acquisition.py:56-420)."""
+
+    _b200_kind = None  # subclasses with a device epilogue set B.ACQ_*
+
+    def __init__(self, random_state=None):
+        if random_state is not None:
+            msg = ("Providing a random_state to an acquisition function during initialization is deprecated "
+                   "and will be ignored. The random_state is instead provided automatically during the "
+                   "suggest() call.")
+            warnings.warn(msg, DeprecationWarning, stacklevel=2)
+        self.i = 0
+
+    @abc.abstractmethod
+    def base_acq(self, *args, **kwargs):
+        """Provide access to the base acquisition function."""
+
+    def _fit_gp(self, gp, target_space):
+        """R/bayes_opt/acquisition.py:79-86."""
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            gp.fit(target_space.params, target_space.target)
+            if target_space.constraint is not None:
+                target_space.constraint.fit(target_space.params, target_space._constraint_values)
+
+    def get_acquisition_params(self):
+        raise NotImplementedError(
+            "Custom AcquisitionFunction subclasses must implement their own get_acquisition_params method.")
+
+    def set_acquisition_params(self, params):
+        raise NotImplementedError(
+            "Custom AcquisitionFunction subclasses must implement their own set_acquisition_params method.")
+
+    def suggest(self, gp, target_space, n_random=10_000, n_smart=10, fit_gp=True, random_state=None):
+        """R/bayes_opt/acquisition.py:116-169."""
+        random_state = ensure_rng(random_state)
+        if len(target_space) == 0:
+            msg = ("Cannot suggest a point without previous samples. Use "
+                   " target_space.random_sample() to generate a point and "
+                   " target_space.probe(*) to evaluate it.")
+            raise TargetSpaceEmptyError(msg)
+        self.i += 1
+        if fit_gp:
+            self._fit_gp(gp=gp, target_space=target_space)
+        acq = self._get_acq(gp=gp, constraint=target_space.constraint)
+        return self._acq_min(acq, target_space, n_random=n_random, n_smart=n_smart, random_state=random_state)
+
+    # -- device closure ------------------------------------------------------------------
+    def _acq_params(self):
+        return {}
+
+    def _get_acq(self, gp, constraint=None):
+        """R/bayes_opt/acquisition.py:171-219, fused on the device."""
+        if self._b200_kind is None:
+            return self._get_acq_generic(gp, constraint)
+        return FusedAcquisition(self._b200_kind, gp, constraint, **self._acq_params())
+
+    def _get_acq_generic(self, gp, constraint=None):
+        """Custom ``base_acq`` written in numpy by a user subclass: mu/sigma (and the constraint
+        probabilities) still come from the device; only the user's O(M) formula runs on host."""
+        gp = _as_b200_gp(gp)
+        dim = gp.X_train_.shape[1]
+
+        def acq(x):
+            x = np.asarray(x, dtype=float).reshape(-1, dim)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                mean, std = gp.predict(x, return_std=True)
+                if constraint is not None:
+                    return -1 * self.base_acq(mean, std) * constraint.predict(x)
+            return -1 * self.base_acq(mean, std)
+
+        return acq
+
+    def _acq_min(self, acq, space, random_state, n_random=10_000, n_smart=10):
+        """R/bayes_opt/acquisition.py:221-272."""
+        if n_random == 0 and n_smart == 0:
+            raise ValueError("Either n_random or n_smart needs to be greater than 0.")
+        x_min_r, min_acq_r, x_seeds = self._random_sample_minimize(
+            acq, space, random_state, n_random=max(n_random, n_smart), n_x_seeds=n_smart)
+        if n_smart:
+            x_min_s, min_acq_s = self._smart_minimize(acq, space, x_seeds=x_seeds, random_state=random_state)
+            if min_acq_r > min_acq_s:
+                return x_min_s
+        return x_min_r
+
+    def _random_sample_minimize(self, acq, space, random_state, n_random, n_x_seeds=0):
+        """R/bayes_opt/acquisition.py:274-320; evaluation + argmin + top-k on the device."""
+        if n_random == 0:
+            return None, np.inf, space.random_sample(n_x_seeds, random_state=random_state)
+        x_tries = space.random_sample(n_random, random_state=random_state)
+        if isinstance(acq, FusedAcquisition):
+            idx, min_acq, top = acq.argmin_topk(x_tries, n_x_seeds)
+            x_min = x_tries[idx]
+            x_seeds = x_tries[top] if n_x_seeds != 0 else []
+            return x_min, min_acq, x_seeds
+        ys = acq(x_tries)
+        x_min = x_tries[ys.argmin()]
+        min_acq = ys.min()
+        if n_x_seeds != 0:
+            idxs = np.argsort(ys)[:n_x_seeds]
+            x_seeds = x_tries[idxs]
+        else:
+            x_seeds = []
+        return x_min, min_acq, x_seeds
+
+    def _smart_minimize(self, acq, space, x_seeds, random_state):
+        """R/bayes_opt/acquisition.py:322-420, continuous branch (:364-374): n_smart L-BFGS-B runs
+        with SciPy's finite-difference gradient; every objective evaluation is a device call."""
+        continuous_dimensions = space.continuous_dimensions
+        continuous_bounds = space.bounds[continuous_dimensions]
+        min_acq = None
+        x_min = None
+        if all(continuous_dimensions):
+            for x_try in x_seeds:
+                res = minimize(acq, x_try, bounds=continuous_bounds, method="L-BFGS-B")
+                if not res.success:
+                    continue
+                if min_acq is None or np.squeeze(res.fun) < min_acq:
+                    x_try = res.x
+                    x_min = x_try
+                    min_acq = np.squeeze(res.fun)
+        else:
+            raise NotImplementedError(
+                "mixed-integer acquisition optimisation (DifferentialEvolutionSolver branch, "
+                "R/bayes_opt/acquisition.py:376-412) is not on the accelerated path yet")
+        if min_acq is None:
+            min_acq = np.inf
+            x_min = np.array([np.nan] * space.bounds.shape[0])
+        return np.clip(x_min, space.bounds[:, 0], space.bounds[:, 1]), min_acq
+
+
+def _check_decay(exploration_decay, exploration_decay_delay):
+    if exploration_decay is not None and not (0 < exploration_decay <= 1):
+        raise ValueError("exploration_decay must be greater than 0 and less than or equal to 1.")
+    if exploration_decay_delay is not None and (
+        not isinstance(exploration_decay_delay, int) or exploration_decay_delay < 0
+    ):
+        raise ValueError("exploration_decay_delay must be an integer greater than or equal to 0.")
+
+
+class UpperConfidenceBound(AcquisitionFunction):
+    """mu + kappa*sigma (R/bayes_opt/acquisition.py:423-580)."""
+
+    _b200_kind = B.ACQ_UCB
+
+    def __init__(self, kappa=2.576, exploration_decay=None, exploration_decay_delay=None, random_state=None):
+        if kappa < 0:
+            raise ValueError("kappa must be greater than or equal to 0.")
+        _check_decay(exploration_decay, exploration_decay_delay)
+        super().__init__(random_state=random_state)
+        self.kappa = kappa
+        self.exploration_decay = exploration_decay
+        self.exploration_decay_delay = exploration_decay_delay
+
+    def base_acq(self, mean, std):
+        return mean + self.kappa * std
+
+    def _acq_params(self):
+        return dict(kappa=self.kappa)
+
+    def suggest(self, gp, target_space, n_random=10_000, n_smart=10, fit_gp=True, random_state=None):
+        if target_space.constraint is not None:
+            msg = (f"Received constraints, but acquisition function {type(self)} "
+                   "does not support constrained optimization.")
+            raise ConstraintNotSupportedError(msg)
+        x_max = super().suggest(gp=gp, target_space=target_space, n_random=n_random, n_smart=n_smart,
+                                fit_gp=fit_gp, random_state=random_state)
+        self.decay_exploration()
+        return x_max
+
+    def decay_exploration(self):
+        if self.exploration_decay is not None and (
+            self.exploration_decay_delay is None or self.exploration_decay_delay <= self.i
+        ):
+            self.kappa = self.kappa * self.exploration_decay
+
+    def get_acquisition_params(self):
+        return {"kappa": self.kappa, "exploration_decay": self.exploration_decay,
+                "exploration_decay_delay": self.exploration_decay_delay}
+
+    def set_acquisition_params(self, params):
+        self.kappa = params["kappa"]
+        self.exploration_decay = params["exploration_decay"]
+        self.exploration_decay_delay = params["exploration_decay_delay"]
+
+
+class _XiAcquisition(AcquisitionFunction):
+    """Shared body of PoI / EI (R/bayes_opt/acquisition.py:583-760, :763-949)."""
+
+    def __init__(self, xi, exploration_decay=None, exploration_decay_delay=None, random_state=None):
+        if xi < 0:
+            raise ValueError("xi must be greater than or equal to 0.")
+        _check_decay(exploration_decay, exploration_decay_delay)
+        super().__init__(random_state=random_state)
+        self.xi = xi
+        self.exploration_decay = exploration_decay
+        self.exploration_decay_delay = exploration_decay_delay
+        self.y_max = None
+
+    def _acq_params(self):
+        if self.y_max is None:
+            raise ValueError("y_max is not set. If you are calling this method outside "
+                             "of suggest(), you must set y_max manually.")
+        return dict(xi=self.xi, y_max=self.y_max)
+
+    def suggest(self, gp, target_space, n_random=10_000, n_smart=10, fit_gp=True, random_state=None):
+        y_max = target_space._target_max()
+        if y_max is None and not target_space.empty:
+            msg = ("Cannot suggest a point without an allowed point. Use "
+                   "target_space.random_sample() to generate a point until "
+                   " at least one point that satisfies the constraints is found.")
+            raise NoValidPointRegisteredError(msg)
+        self.y_max = y_max
+        x_max = super().suggest(gp=gp, target_space=target_space, n_random=n_random, n_smart=n_smart,
+                                fit_gp=fit_gp, random_state=random_state)
+        self.decay_exploration()
+        return x_max
+
+    def decay_exploration(self):
+        if self.exploration_decay is not None and (
+            self.exploration_decay_delay is None or self.exploration_decay_delay <= self.i
+        ):
+            self.xi = self.xi * self.exploration_decay
+
+    def get_acquisition_params(self):
+        return {"xi": self.xi, "exploration_decay": self.exploration_decay,
+                "exploration_decay_delay": self.exploration_decay_delay}
+
+    def set_acquisition_params(self, params):
+        self.xi = params["xi"]
+        self.exploration_decay = params["exploration_decay"]
+        self.exploration_decay_delay = params["exploration_decay_delay"]
+
+
+class ProbabilityOfImprovement(_XiAcquisition):
+    """Phi((mu - y_max - xi)/sigma) (R/bayes_opt/acquisition.py:633-661)."""
+
+    _b200_kind = B.ACQ_POI
+
+    def base_acq(self, mean, std):
+        if self.y_max is None:
+            raise ValueError("y_max is not set. If you are calling this method outside "
+                             "of suggest(), you must set y_max manually.")
+        z = (mean - self.y_max - self.xi) / std
+        return norm.cdf(z)
+
+
+class ExpectedImprovement(_XiAcquisition):
+    """a*Phi(a/sigma) + sigma*phi(a/sigma), a = mu - y_max - xi (R/bayes_opt/acquisition.py:820-849)."""
+
+    _b200_kind = B.ACQ_EI
+
+    def base_acq(self, mean, std):
+        if self.y_max is None:
+            raise ValueError("y_max is not set. If you are calling this method outside "
+                             "of suggest(), ensure y_max is set, or set it manually.")
+        a = mean - self.y_max - self.xi
+        z = a / std
+        return a * norm.cdf(z) + std * norm.pdf(z)
+
+
+class ConstantLiar(AcquisitionFunction):
+    """R/bayes_opt/acquisition.py:952-1178: re-fit on a copy of the space that contains the
+    pending suggestions with a lied-about target, then delegate to the base acquisition."""
+
+    def __init__(self, base_acquisition, strategy="max", random_state=None, atol=1e-5, rtol=1e-8):
+        super().__init__(random_state)
+        self.base_acquisition = base_acquisition
+        self.dummies = []
+        if not isinstance(strategy, float) and strategy not in ["min", "mean", "max"]:
+            raise ValueError(f"Received invalid argument {strategy} for strategy.")
+        self.strategy = strategy
+        self.atol = atol
+        self.rtol = rtol
+
+    def base_acq(self, *args, **kwargs):
+        return self.base_acquisition.base_acq(*args, **kwargs)
+
+    def _copy_target_space(self, target_space):
+        """R/bayes_opt/acquisition.py:1013-1037."""
+        keys = target_space.keys
+        pbounds = {key: bound for key, bound in zip(keys, target_space.bounds)}
+        target_space_copy = type(target_space)(
+            None, pbounds=pbounds, allow_duplicate_points=target_space._allow_duplicate_points)
+        if target_space._constraint is not None:
+            target_space_copy.set_constraint(deepcopy(target_space.constraint))
+        target_space_copy._params = deepcopy(target_space._params)
+        target_space_copy._target = deepcopy(target_space._target)
+        return target_space_copy
+
+    def _remove_expired_dummies(self, target_space):
+        """R/bayes_opt/acquisition.py:1039-1056."""
+        dummies = []
+        for dummy in self.dummies:
+            close = np.isclose(dummy, target_space.params, rtol=self.rtol, atol=self.atol)
+            if not close.all(axis=1).any():
+                dummies.append(dummy)
+        self.dummies = dummies
+
+    def suggest(self, gp, target_space, n_random=10_000, n_smart=10, fit_gp=True, random_state=None):
+        if len(target_space) == 0:
+            msg = ("Cannot suggest a point without previous samples. Use "
+                   " target_space.random_sample() to generate a point and "
+                   " target_space.probe(*) to evaluate it.")
+            raise TargetSpaceEmptyError(msg)
+        if target_space.constraint is not None:
+            msg = (f"Received constraints, but acquisition function {type(self)} "
+                   "does not support constrained optimization.")
+            raise ConstraintNotSupportedError(msg)
+        self._remove_expired_dummies(target_space)
+        dummy_target_space = self._copy_target_space(target_space)
+        if isinstance(self.strategy, float):
+            dummy_target = self.strategy
+        elif self.strategy == "min":
+            dummy_target = target_space.target.min()
+        elif self.strategy == "mean":
+            dummy_target = target_space.target.mean()
+        elif self.strategy != "max":
+            raise ValueError(f"Received invalid argument {self.strategy} for strategy.")
+        else:
+            dummy_target = target_space.target.max()
+        for dummy in self.dummies:
+            dummy_target_space.register(dummy, dummy_target)
+        self._fit_gp(gp=gp, target_space=dummy_target_space)
+        x_max = self.base_acquisition.suggest(gp, dummy_target_space, n_random=n_random, n_smart=n_smart,
+                                              fit_gp=False, random_state=random_state)
+        self.dummies.append(x_max)
+        return x_max
+
+    def get_acquisition_params(self):
+        return {"dummies": [dummy.tolist() for dummy in self.dummies],
+                "base_acquisition_params": self.base_acquisition.get_acquisition_params(),
+                "strategy": self.strategy, "atol": self.atol, "rtol": self.rtol}
+
+    def set_acquisition_params(self, params):
+        self.dummies = [np.array(dummy) for dummy in params["dummies"]]
+        self.base_acquisition.set_acquisition_params(params["base_acquisition_params"])
+        self.strategy = params["strategy"]
+        self.atol = params["atol"]
+        self.rtol = params["rtol"]

@@ -1,0 +1,650 @@
+// b200bo.cu - C ABI (include/b200bo.h) over the sm_100a kernels.  No CPU fallback: every
+// compute entry point needs a CUDA device and reports B200BO_ERR_CUDA without one.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "fit_kernels.cuh"
+#include "predict_kernels.cuh"
+
+using namespace b200bo;
+
+// ---------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return set_err(B200BO_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                  \
+                           cudaGetErrorString(e__), __FILE__, __LINE__);                      \
+    } while (0)
+
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+// ---------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return B200BO_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess)
+            return set_err(B200BO_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cap = bytes;
+        return B200BO_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+struct b200bo_gp {
+    int device = 0;
+    int sm_count = 0;
+    long long n = 0;
+    int np = 0, d = 0;
+    bool has_data = false, fitted = false;
+    // kernel of the last fit
+    int family = 0, nu = B200BO_NU_25;
+    double constv = 1.0, jitter = 0.0;
+    double y_mean = 0.0, y_std = 1.0;
+    std::vector<double> y_norm;  // host copy of normalised targets (n)
+    std::vector<int> xform;      // host copy (d) or empty
+    DevBuf X, Xs, y, K, L, W, WT, T, alphav, v1, v2, ls, xf, info, part;
+    // predict-side scratch (used when this handle is gps[0] of a call)
+    DevBuf pscratch, xc, out_acq, out_mu, out_sd, sel, clamp;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+static thread_local b200bo_gp* g_last_timed = nullptr;
+
+static inline int round_up(long long v, int m) { return (int)(((v + m - 1) / m) * m); }
+
+extern "C" int b200bo_version(void) { return B200BO_VERSION; }
+extern "C" const char* b200bo_last_error(void) { return g_err; }
+extern "C" int64_t b200bo_launch_count(void) { return g_launches.load(); }
+
+extern "C" int b200bo_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int b200bo_gp_create(b200bo_gp** out, int device) {
+    if (!out) return set_err(B200BO_ERR_ARG, "out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_err(B200BO_ERR_CUDA,
+                       "no CUDA device available (%s); this engine has no CPU fallback",
+                       e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= ndev) return set_err(B200BO_ERR_ARG, "device %d out of range", device);
+    CU(cudaSetDevice(device));
+    b200bo_gp* gp = new b200bo_gp();
+    gp->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    gp->sm_count = prop.multiProcessorCount;
+    CU(cudaEventCreate(&gp->ev0));
+    CU(cudaEventCreate(&gp->ev1));
+    CU(cudaFuncSetAttribute(predict_acq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            kPredictSmemBytes));
+    CU(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            kPotrfSmemBytes));
+    *out = gp;
+    return B200BO_OK;
+}
+
+extern "C" void b200bo_gp_destroy(b200bo_gp* gp) {
+    if (!gp) return;
+    cudaSetDevice(gp->device);
+    DevBuf* bufs[] = {&gp->X, &gp->Xs, &gp->y, &gp->K, &gp->L, &gp->W, &gp->WT, &gp->T,
+                      &gp->alphav, &gp->v1, &gp->v2, &gp->ls, &gp->xf, &gp->info, &gp->part,
+                      &gp->pscratch, &gp->xc, &gp->out_acq, &gp->out_mu, &gp->out_sd, &gp->sel,
+                      &gp->clamp};
+    for (DevBuf* b : bufs) b->release();
+    if (gp->ev0) cudaEventDestroy(gp->ev0);
+    if (gp->ev1) cudaEventDestroy(gp->ev1);
+    if (g_last_timed == gp) g_last_timed = nullptr;
+    delete gp;
+}
+
+extern "C" int64_t b200bo_gp_n(const b200bo_gp* gp) { return gp ? gp->n : 0; }
+extern "C" int b200bo_gp_dim(const b200bo_gp* gp) { return gp ? gp->d : 0; }
+
+extern "C" int b200bo_gp_set_transform(b200bo_gp* gp, const int32_t* xform, int d) {
+    if (!gp) return set_err(B200BO_ERR_ARG, "gp is NULL");
+    gp->xform.clear();
+    if (xform) {
+        if (d <= 0 || d > B200BO_MAX_DIM) return set_err(B200BO_ERR_ARG, "bad d=%d", d);
+        for (int j = 0; j < d; ++j) {
+            if (xform[j] != B200BO_XFORM_IDENTITY && xform[j] != B200BO_XFORM_ROUND)
+                return set_err(B200BO_ERR_UNSUPPORTED, "transform code %d unsupported", xform[j]);
+            gp->xform.push_back(xform[j]);
+        }
+    }
+    gp->fitted = false;
+    return B200BO_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// data upload + y normalisation (SK/gaussian_process/_gpr.py:275-285)
+// ---------------------------------------------------------------------------------------
+extern "C" int b200bo_gp_set_data(b200bo_gp* gp, const double* X, const double* y, int64_t n, int d,
+                                  int normalize_y) {
+    if (!gp || !X || !y) return set_err(B200BO_ERR_ARG, "NULL argument");
+    if (n <= 0 || d <= 0 || d > B200BO_MAX_DIM)
+        return set_err(B200BO_ERR_ARG, "bad shape n=%lld d=%d (d <= %d)", (long long)n, d, B200BO_MAX_DIM);
+    if (n > 46000) return set_err(B200BO_ERR_ARG, "n=%lld too large", (long long)n);
+    if (!gp->xform.empty() && (int)gp->xform.size() != d)
+        return set_err(B200BO_ERR_ARG, "transform has %zu entries, d=%d", gp->xform.size(), d);
+    CU(cudaSetDevice(gp->device));
+    gp->fitted = false;
+    gp->n = n;
+    gp->d = d;
+    gp->np = round_up(n, kPad);
+    const size_t np = gp->np;
+    // y statistics in the order numpy uses for small arrays is irrelevant at 1e-16; use
+    // a compensated sum so the result is the correctly rounded mean / population std.
+    double mean = 0.0, sd = 1.0;
+    gp->y_norm.assign(y, y + n);
+    if (normalize_y) {
+        long double s = 0.0L;
+        for (int64_t i = 0; i < n; ++i) s += y[i];
+        mean = (double)(s / (long double)n);
+        long double q = 0.0L;
+        for (int64_t i = 0; i < n; ++i) {
+            const long double t = (long double)y[i] - (long double)mean;
+            q += t * t;
+        }
+        sd = (double)sqrtl(q / (long double)n);
+        if (sd == 0.0) sd = 1.0;
+        for (int64_t i = 0; i < n; ++i) gp->y_norm[i] = (y[i] - mean) / sd;
+    }
+    gp->y_mean = mean;
+    gp->y_std = sd;
+    int rc;
+    if ((rc = gp->X.reserve(sizeof(double) * n * d))) return rc;
+    if ((rc = gp->Xs.reserve(sizeof(double) * np * d))) return rc;
+    if ((rc = gp->y.reserve(sizeof(double) * np))) return rc;
+    if ((rc = gp->alphav.reserve(sizeof(double) * np))) return rc;
+    if ((rc = gp->v1.reserve(sizeof(double) * np))) return rc;
+    if ((rc = gp->v2.reserve(sizeof(double) * np))) return rc;
+    if ((rc = gp->ls.reserve(sizeof(double) * B200BO_MAX_DIM))) return rc;
+    if ((rc = gp->xf.reserve(sizeof(int) * B200BO_MAX_DIM))) return rc;
+    if ((rc = gp->info.reserve(sizeof(int)))) return rc;
+    if ((rc = gp->K.reserve(sizeof(double) * np * np))) return rc;
+    if ((rc = gp->L.reserve(sizeof(double) * np * np))) return rc;
+    if ((rc = gp->W.reserve(sizeof(double) * np * np))) return rc;
+    if ((rc = gp->WT.reserve(sizeof(double) * np * np))) return rc;
+    if ((rc = gp->T.reserve(sizeof(double) * np * np))) return rc;
+    CU(cudaMemcpy(gp->X.p, X, sizeof(double) * n * d, cudaMemcpyHostToDevice));
+    CU(cudaMemset(gp->y.p, 0, sizeof(double) * np));
+    CU(cudaMemcpy(gp->y.p, gp->y_norm.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    if (!gp->xform.empty())
+        CU(cudaMemcpy(gp->xf.p, gp->xform.data(), sizeof(int) * d, cudaMemcpyHostToDevice));
+    gp->has_data = true;
+    return B200BO_OK;
+}
+
+static int check_kernel(const b200bo_gp* gp, const b200bo_kernel* k) {
+    if (!k || !k->length_scale) return set_err(B200BO_ERR_ARG, "kernel/length_scale is NULL");
+    if (k->family != B200BO_KERNEL_MATERN && k->family != B200BO_KERNEL_RBF)
+        return set_err(B200BO_ERR_UNSUPPORTED, "kernel family %d unsupported", k->family);
+    if (k->family == B200BO_KERNEL_MATERN && (k->nu < B200BO_NU_05 || k->nu > B200BO_NU_INF))
+        return set_err(B200BO_ERR_UNSUPPORTED, "Matern nu code %d unsupported", k->nu);
+    if (k->n_length_scale != 1 && k->n_length_scale != gp->d)
+        return set_err(B200BO_ERR_ARG, "n_length_scale=%d must be 1 or d=%d", k->n_length_scale, gp->d);
+    for (int j = 0; j < k->n_length_scale; ++j)
+        if (!(k->length_scale[j] > 0.0)) return set_err(B200BO_ERR_ARG, "length_scale must be > 0");
+    if (!(k->const_value > 0.0)) return set_err(B200BO_ERR_ARG, "const_value must be > 0");
+    return B200BO_OK;
+}
+
+template <bool TA, bool TB>
+static int gemm(int M, int N, int K, double alpha, const double* A, int lda, long long sA,
+                const double* B, int ldb, long long sB, double beta, double* C, int ldc,
+                long long sC, int batch, int lower_only, int kmode) {
+    if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return B200BO_OK;
+    dim3 grid(N / 64, M / 64, batch);
+    dgemm64_kernel<TA, TB><<<grid, 256>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC,
+                                          lower_only, kmode);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return B200BO_OK;
+}
+
+// K build + Cholesky + explicit triangular inverse.  On return L holds the clean lower factor,
+// W = L^-1 (lower).  *info_out = 0 or the failing pivot (1-based).
+static int factorize(b200bo_gp* gp, const b200bo_kernel* kern, double jitter, int* info_out) {
+    const int n = (int)gp->n, np = gp->np, d = gp->d;
+    double ls[B200BO_MAX_DIM];
+    for (int j = 0; j < d; ++j) ls[j] = kern->length_scale[kern->n_length_scale == 1 ? 0 : j];
+    CU(cudaMemcpy(gp->ls.p, ls, sizeof(double) * d, cudaMemcpyHostToDevice));
+    const int* xf = gp->xform.empty() ? nullptr : gp->xf.as<int>();
+    {
+        const long long tot = (long long)np * d;
+        scale_x_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(gp->X.as<double>(), gp->ls.as<double>(), xf,
+                                                               gp->Xs.as<double>(), n, np, d);
+        LAUNCHED();
+    }
+    {
+        dim3 blk(32, 8), grd((np + 31) / 32, (np + 7) / 8);
+        kbuild_kernel<<<grd, blk>>>(gp->Xs.as<double>(), gp->K.as<double>(), n, np, d, kern->family,
+                                    kern->family == B200BO_KERNEL_RBF ? B200BO_NU_INF : kern->nu,
+                                    kern->const_value, jitter);
+        LAUNCHED();
+    }
+    CU(cudaGetLastError());
+    double* L = gp->L.as<double>();
+    double* W = gp->W.as<double>();
+    double* T = gp->T.as<double>();
+    CU(cudaMemcpyAsync(L, gp->K.p, sizeof(double) * (size_t)np * np, cudaMemcpyDeviceToDevice));
+    CU(cudaMemsetAsync(W, 0, sizeof(double) * (size_t)np * np));
+    CU(cudaMemsetAsync(gp->info.p, 0, sizeof(int)));
+    int rc;
+    // right-looking blocked Cholesky, panel width 64
+    for (int j0 = 0; j0 < np; j0 += 64) {
+        potrf_diag_kernel<<<1, 256, kPotrfSmemBytes>>>(L, np, j0, W + (size_t)j0 * np + j0, np, gp->info.as<int>());
+        LAUNCHED();
+        const int below = np - j0 - 64;
+        if (below > 0) {
+            double* panel = L + (size_t)(j0 + 64) * np + j0;
+            // L_ij = A_ij * inv(L_jj)^T
+            if ((rc = gemm<false, true>(below, 64, 64, 1.0, panel, np, 0, W + (size_t)j0 * np + j0, np, 0,
+                                        0.0, panel, np, 0, 1, 0, 0)))
+                return rc;
+            // trailing update (lower tiles only): A_ik -= L_ij L_kj^T
+            if ((rc = gemm<false, true>(below, below, 64, -1.0, panel, np, 0, panel, np, 0, 1.0,
+                                        L + (size_t)(j0 + 64) * np + j0 + 64, np, 0, 1, 1, 0)))
+                return rc;
+        }
+    }
+    {
+        dim3 blk(32, 8), grd((np + 31) / 32, (np + 7) / 8);
+        zero_upper_kernel<<<grd, blk>>>(L, np);
+        LAUNCHED();
+    }
+    int info = 0;
+    CU(cudaMemcpy(&info, gp->info.p, sizeof(int), cudaMemcpyDeviceToHost));
+    *info_out = info;
+    if (info != 0) return B200BO_OK;
+    // W = L^-1 by recursive doubling over diagonal blocks:
+    //   inv([[A,0],[C,B]]) = [[A^-1,0],[-B^-1 C A^-1, B^-1]]
+    for (int s = 64; s < np; s *= 2) {
+        const int full = np / (2 * s);
+        const int rem = np % (2 * s);
+        const long long stride = (long long)2 * s * ((long long)np + 1);
+        if (full > 0) {
+            // T = C * A^-1      (A^-1 lower-triangular: k >= n0)
+            if ((rc = gemm<false, false>(s, s, s, 1.0, L + (size_t)s * np, np, stride, W, np, stride, 0.0,
+                                         T + (size_t)s * np, np, stride, full, 0, 2)))
+                return rc;
+            // W21 = -B^-1 * T   (B^-1 lower-triangular: k < m0 + 64)
+            if ((rc = gemm<false, false>(s, s, s, -1.0, W + (size_t)s * np + s, np, stride,
+                                         T + (size_t)s * np, np, stride, 0.0, W + (size_t)s * np, np,
+                                         stride, full, 0, 1)))
+                return rc;
+        }
+        if (rem > s) {
+            const int m2 = rem - s;
+            const size_t o = (size_t)full * 2 * s;
+            const double* C = L + (o + s) * np + o;
+            double* Tt = T + (o + s) * np + o;
+            if ((rc = gemm<false, false>(m2, s, s, 1.0, C, np, 0, W + o * np + o, np, 0, 0.0, Tt, np, 0, 1,
+                                         0, 2)))
+                return rc;
+            if ((rc = gemm<false, false>(m2, s, m2, -1.0, W + (o + s) * np + o + s, np, 0, Tt, np, 0, 0.0,
+                                         W + (o + s) * np + o, np, 0, 1, 0, 1)))
+                return rc;
+        }
+    }
+    CU(cudaGetLastError());
+    return B200BO_OK;
+}
+
+static int transpose_W(b200bo_gp* gp) {
+    const int np = gp->np;
+    dim3 blk(32, 8), grd(np / 32, np / 32);
+    transpose_kernel<<<grd, blk>>>(gp->W.as<double>(), gp->WT.as<double>(), np);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return B200BO_OK;
+}
+
+// alpha_ = K^-1 y via the explicit inverse factors + one step of iterative refinement
+static int solve_alpha(b200bo_gp* gp) {
+    const int np = gp->np;
+    const int wpb = 8;  // warps per block
+    dim3 blk(32 * wpb), grd((np + wpb - 1) / wpb);
+    double* a = gp->alphav.as<double>();
+    double* v1 = gp->v1.as<double>();
+    double* v2 = gp->v2.as<double>();
+    const double* y = gp->y.as<double>();
+    // z = W y ; a = W^T z
+    gemv_rows_kernel<<<grd, blk>>>(gp->W.as<double>(), np, y, v1, np, np, 1);
+    gemv_rows_kernel<<<grd, blk>>>(gp->WT.as<double>(), np, v1, a, np, np, 2);
+    // r = y - K a ; a += W^T W r
+    gemv_rows_kernel<<<grd, blk>>>(gp->K.as<double>(), np, a, v1, np, np, 0);
+    residual_kernel<<<(np + 255) / 256, 256>>>(y, v1, np);
+    gemv_rows_kernel<<<grd, blk>>>(gp->W.as<double>(), np, v1, v2, np, np, 1);
+    gemv_rows_kernel<<<grd, blk>>>(gp->WT.as<double>(), np, v2, v1, np, np, 2);
+    axpy1_kernel<<<(np + 255) / 256, 256>>>(a, v1, np);
+    for (int i = 0; i < 7; ++i) LAUNCHED();
+    CU(cudaGetLastError());
+    return B200BO_OK;
+}
+
+extern "C" int b200bo_gp_fit(b200bo_gp* gp, const double* X, const double* y, int64_t n, int d,
+                             const b200bo_kernel* kern, double alpha, int normalize_y, int64_t* info) {
+    int rc;
+    if ((rc = b200bo_gp_set_data(gp, X, y, n, d, normalize_y))) return rc;
+    if ((rc = check_kernel(gp, kern))) return rc;
+    if (info) *info = 0;
+    int finfo = 0;
+    if ((rc = factorize(gp, kern, alpha, &finfo))) return rc;
+    if (finfo != 0) {
+        if (info) *info = finfo;
+        return set_err(B200BO_ERR_NOT_PD, "%d-th leading minor of the array is not positive definite", finfo);
+    }
+    if ((rc = transpose_W(gp))) return rc;
+    if ((rc = solve_alpha(gp))) return rc;
+    CU(cudaDeviceSynchronize());
+    gp->family = kern->family;
+    gp->nu = kern->family == B200BO_KERNEL_RBF ? B200BO_NU_INF : kern->nu;
+    gp->constv = kern->const_value;
+    gp->jitter = alpha;
+    gp->fitted = true;
+    return B200BO_OK;
+}
+
+extern "C" int b200bo_gp_lml(b200bo_gp* gp, const b200bo_kernel* kern, double alpha, int has_const,
+                             double* lml, double* grad) {
+    if (!gp || !lml) return set_err(B200BO_ERR_ARG, "NULL argument");
+    if (!gp->has_data) return set_err(B200BO_ERR_STATE, "no training data: call b200bo_gp_set_data");
+    int rc;
+    if ((rc = check_kernel(gp, kern))) return rc;
+    CU(cudaSetDevice(gp->device));
+    gp->fitted = false;  // buffers are being overwritten
+    const int n = (int)gp->n, np = gp->np, d = gp->d;
+    const int aniso = kern->n_length_scale > 1;
+    const int ntheta = (has_const ? 1 : 0) + kern->n_length_scale;
+    int finfo = 0;
+    if ((rc = factorize(gp, kern, alpha, &finfo))) return rc;
+    if (finfo != 0) {  // SK/_gpr.py:590-593
+        *lml = -std::numeric_limits<double>::infinity();
+        if (grad)
+            for (int p = 0; p < ntheta; ++p) grad[p] = 0.0;
+        return B200BO_OK;
+    }
+    if ((rc = transpose_W(gp))) return rc;
+    if ((rc = solve_alpha(gp))) return rc;
+    diag_kernel<<<(n + 255) / 256, 256>>>(gp->L.as<double>(), np, gp->v1.as<double>(), n);
+    LAUNCHED();
+    std::vector<double> a(n), dg(n);
+    CU(cudaMemcpy(a.data(), gp->alphav.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(dg.data(), gp->v1.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    long double ya = 0.0L, ld = 0.0L;
+    for (int i = 0; i < n; ++i) {
+        ya += (long double)gp->y_norm[i] * a[i];
+        ld += logl((long double)dg[i]);
+    }
+    *lml = (double)(-0.5L * ya - ld - (long double)n / 2.0L * logl(2.0L * 3.14159265358979323846264338327950288L));
+    if (grad) {
+        // Kinv = W^T W  (W lower: k >= max(m0, n0))
+        if ((rc = gemm<true, false>(np, np, np, 1.0, gp->W.as<double>(), np, 0, gp->W.as<double>(), np, 0,
+                                    0.0, gp->T.as<double>(), np, 0, 1, 0, 3)))
+            return rc;
+        dim3 grd((n + 15) / 16, (n + 15) / 16);
+        const size_t nblk = (size_t)grd.x * grd.y;
+        if ((rc = gp->part.reserve(sizeof(double) * nblk * ntheta))) return rc;
+        lml_grad_kernel<<<grd, 256>>>(gp->Xs.as<double>(), gp->T.as<double>(), np, gp->alphav.as<double>(),
+                                      n, d, kern->family,
+                                      kern->family == B200BO_KERNEL_RBF ? B200BO_NU_INF : kern->nu,
+                                      kern->const_value, has_const, aniso, gp->part.as<double>(), ntheta);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        std::vector<double> part(nblk * ntheta);
+        CU(cudaMemcpy(part.data(), gp->part.p, sizeof(double) * nblk * ntheta, cudaMemcpyDeviceToHost));
+        for (int p = 0; p < ntheta; ++p) {
+            long double s = 0.0L;
+            for (size_t b = 0; b < nblk; ++b) s += part[b * ntheta + p];
+            grad[p] = (double)s;
+        }
+    }
+    return B200BO_OK;
+}
+
+extern "C" int b200bo_gp_get(b200bo_gp* gp, int what, double* out, int64_t len) {
+    if (!gp || !out) return set_err(B200BO_ERR_ARG, "NULL argument");
+    if (!gp->fitted) return set_err(B200BO_ERR_STATE, "GP handle is not fitted");
+    CU(cudaSetDevice(gp->device));
+    const size_t n = gp->n, np = gp->np;
+    const void* src = nullptr;
+    switch (what) {
+        case B200BO_GET_L: src = gp->L.p; break;
+        case B200BO_GET_K: src = gp->K.p; break;
+        case B200BO_GET_LINV: src = gp->W.p; break;
+        case B200BO_GET_ALPHA:
+            if (len != (int64_t)n) return set_err(B200BO_ERR_ARG, "len must be n");
+            CU(cudaMemcpy(out, gp->alphav.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+            return B200BO_OK;
+        case B200BO_GET_YSTATS:
+            if (len != 2) return set_err(B200BO_ERR_ARG, "len must be 2");
+            out[0] = gp->y_mean;
+            out[1] = gp->y_std;
+            return B200BO_OK;
+        default: return set_err(B200BO_ERR_ARG, "unknown selector %d", what);
+    }
+    if (len != (int64_t)(n * n)) return set_err(B200BO_ERR_ARG, "len must be n*n");
+    CU(cudaMemcpy2D(out, sizeof(double) * n, src, sizeof(double) * np, sizeof(double) * n, n,
+                    cudaMemcpyDeviceToHost));
+    return B200BO_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// predict / acquisition
+// ---------------------------------------------------------------------------------------
+static int check_spec(const b200bo_acq* spec) {
+    if (!spec) return set_err(B200BO_ERR_ARG, "spec is NULL");
+    if (spec->n_gps < 1 || spec->n_gps > B200BO_MAX_GPS)
+        return set_err(B200BO_ERR_ARG, "n_gps=%d out of range [1,%d]", spec->n_gps, B200BO_MAX_GPS);
+    if (spec->kind < B200BO_ACQ_UCB || spec->kind > B200BO_ACQ_NONE)
+        return set_err(B200BO_ERR_ARG, "unknown acquisition kind %d", spec->kind);
+    for (int g = 0; g < spec->n_gps; ++g) {
+        const b200bo_gp* gp = spec->gps[g];
+        if (!gp) return set_err(B200BO_ERR_ARG, "gps[%d] is NULL", g);
+        if (!gp->fitted) return set_err(B200BO_ERR_STATE, "gps[%d] is not fitted", g);
+        if (gp->d != spec->gps[0]->d) return set_err(B200BO_ERR_ARG, "gps[%d] has a different dimension", g);
+        if (gp->device != spec->gps[0]->device)
+            return set_err(B200BO_ERR_ARG, "gps[%d] lives on a different device", g);
+        if (g >= 1 && !(spec->lb[g] < spec->ub[g]))
+            return set_err(B200BO_ERR_ARG, "constraint %d: lb must be < ub", g);
+    }
+    return B200BO_OK;
+}
+
+extern "C" int b200bo_acq_eval_dev(const b200bo_acq* spec, const double* d_Xc, int64_t m,
+                                   double* d_acq_neg, double* d_mu, double* d_sd, int k, void* d_sel,
+                                   int64_t index_base, void* stream_) {
+    int rc;
+    if ((rc = check_spec(spec))) return rc;
+    if (m < 0 || (m > 0 && !d_Xc)) return set_err(B200BO_ERR_ARG, "bad candidates");
+    if (k < 0 || k > B200BO_MAX_TOPK) return set_err(B200BO_ERR_ARG, "k=%d out of range", k);
+    if (k > 0 && !d_sel) return set_err(B200BO_ERR_ARG, "d_sel is NULL");
+    b200bo_gp* g0 = spec->gps[0];
+    CU(cudaSetDevice(g0->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    double* acq_buf = d_acq_neg;
+    if (k > 0 && !acq_buf) {
+        if ((rc = g0->out_acq.reserve(sizeof(double) * (size_t)(m > 0 ? m : 1)))) return rc;
+        acq_buf = g0->out_acq.as<double>();
+    }
+    PredictParams P;
+    memset(&P, 0, sizeof(P));
+    int np_max = 0;
+    for (int g = 0; g < spec->n_gps; ++g) {
+        b200bo_gp* gp = spec->gps[g];
+        GpDev& G = P.gp[g];
+        G.Xs = gp->Xs.as<double>();
+        G.linvT = gp->WT.as<double>();
+        G.alphav = gp->alphav.as<double>();
+        G.ls = gp->ls.as<double>();
+        G.xform = gp->xform.empty() ? nullptr : gp->xf.as<int>();
+        G.n = (int)gp->n;
+        G.np = gp->np;
+        G.family = gp->family;
+        G.nu = gp->nu;
+        G.constv = gp->constv;
+        G.y_mean = gp->y_mean;
+        G.y_std = gp->y_std;
+        G.lb = spec->lb[g];
+        G.ub = spec->ub[g];
+        np_max = gp->np > np_max ? gp->np : np_max;
+    }
+    P.n_gps = spec->n_gps;
+    P.d = g0->d;
+    P.acq_kind = spec->kind;
+    P.kappa = spec->kappa;
+    P.xi = spec->xi;
+    P.y_max = spec->y_max;
+    P.Xc = d_Xc;
+    P.m = m;
+    P.acq_out = acq_buf;
+    P.mu_out = d_mu;
+    P.sd_out = d_sd;
+    if ((rc = g0->clamp.reserve(sizeof(unsigned long long)))) return rc;
+    P.clamp_count = g0->clamp.as<unsigned long long>();
+    CU(cudaMemsetAsync(g0->clamp.p, 0, sizeof(unsigned long long), stream));
+    const long long ntiles = (m + PBN - 1) / PBN;
+    int grid = (int)(ntiles < g0->sm_count ? ntiles : g0->sm_count);
+    if (grid > 0) {
+        P.scratch_stride = (long long)np_max * PBN;
+        if ((rc = g0->pscratch.reserve(sizeof(double) * (size_t)P.scratch_stride * g0->sm_count))) return rc;
+        P.scratch = g0->pscratch.as<double>();
+        CU(cudaEventRecord(g0->ev0, stream));
+        predict_acq_kernel<<<grid, PNT, kPredictSmemBytes, stream>>>(P);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(g0->ev1, stream));
+        g_last_timed = g0;
+    }
+    if (k > 0) {
+        select_kernel<<<1, 1024, 0, stream>>>(acq_buf, m, k, reinterpret_cast<SelRecord*>(d_sel), index_base);
+        LAUNCHED();
+        CU(cudaGetLastError());
+    }
+    return B200BO_OK;
+}
+
+extern "C" int b200bo_last_kernel_ms(float* ms) {
+    if (!ms) return set_err(B200BO_ERR_ARG, "ms is NULL");
+    if (!g_last_timed) return set_err(B200BO_ERR_STATE, "no timed kernel on this thread");
+    CU(cudaSetDevice(g_last_timed->device));
+    CU(cudaEventSynchronize(g_last_timed->ev1));
+    CU(cudaEventElapsedTime(ms, g_last_timed->ev0, g_last_timed->ev1));
+    return B200BO_OK;
+}
+
+// host-buffer front end shared by predict / acq_eval / argmin_topk
+static int run_host(const b200bo_acq* spec, const double* Xc, int64_t m, double* acq_neg, double* mu,
+                    double* sd, int k, SelRecord* sel_host, int64_t* n_clamped) {
+    int rc;
+    if ((rc = check_spec(spec))) return rc;
+    if (m < 0 || (m > 0 && !Xc)) return set_err(B200BO_ERR_ARG, "bad candidates");
+    b200bo_gp* g0 = spec->gps[0];
+    CU(cudaSetDevice(g0->device));
+    const size_t mm = (size_t)(m > 0 ? m : 1);
+    if ((rc = g0->xc.reserve(sizeof(double) * mm * g0->d))) return rc;
+    if ((rc = g0->out_acq.reserve(sizeof(double) * mm))) return rc;
+    if (mu && (rc = g0->out_mu.reserve(sizeof(double) * mm))) return rc;
+    if (sd && (rc = g0->out_sd.reserve(sizeof(double) * mm))) return rc;
+    if ((rc = g0->sel.reserve(sizeof(SelRecord) * (B200BO_MAX_TOPK + 1)))) return rc;
+    if (m > 0) CU(cudaMemcpy(g0->xc.p, Xc, sizeof(double) * (size_t)m * g0->d, cudaMemcpyHostToDevice));
+    if ((rc = b200bo_acq_eval_dev(spec, g0->xc.as<double>(), m, g0->out_acq.as<double>(),
+                                  mu ? g0->out_mu.as<double>() : nullptr,
+                                  sd ? g0->out_sd.as<double>() : nullptr, k, g0->sel.p, 0, nullptr)))
+        return rc;
+    CU(cudaDeviceSynchronize());
+    if (m > 0) {
+        if (acq_neg) CU(cudaMemcpy(acq_neg, g0->out_acq.p, sizeof(double) * m, cudaMemcpyDeviceToHost));
+        if (mu) CU(cudaMemcpy(mu, g0->out_mu.p, sizeof(double) * m, cudaMemcpyDeviceToHost));
+        if (sd) CU(cudaMemcpy(sd, g0->out_sd.p, sizeof(double) * m, cudaMemcpyDeviceToHost));
+    }
+    if (k > 0 && sel_host)
+        CU(cudaMemcpy(sel_host, g0->sel.p, sizeof(SelRecord) * (k + 1), cudaMemcpyDeviceToHost));
+    if (n_clamped) {
+        unsigned long long c = 0;
+        CU(cudaMemcpy(&c, g0->clamp.p, sizeof(c), cudaMemcpyDeviceToHost));
+        *n_clamped = (int64_t)c;
+    }
+    return B200BO_OK;
+}
+
+extern "C" int b200bo_gp_predict(b200bo_gp* gp, const double* Xc, int64_t m, double* mu, double* sd,
+                                 int64_t* n_clamped) {
+    if (!gp || !mu) return set_err(B200BO_ERR_ARG, "NULL argument");
+    b200bo_acq spec;
+    memset(&spec, 0, sizeof(spec));
+    spec.kind = B200BO_ACQ_NONE;
+    spec.n_gps = 1;
+    spec.gps[0] = gp;
+    return run_host(&spec, Xc, m, nullptr, mu, sd, 0, nullptr, n_clamped);
+}
+
+extern "C" int b200bo_acq_eval(const b200bo_acq* spec, const double* Xc, int64_t m, double* acq_neg) {
+    if (!acq_neg && m > 0) return set_err(B200BO_ERR_ARG, "acq_neg is NULL");
+    if (spec && spec->kind == B200BO_ACQ_NONE) return set_err(B200BO_ERR_ARG, "kind NONE has no acquisition");
+    return run_host(spec, Xc, m, acq_neg, nullptr, nullptr, 0, nullptr, nullptr);
+}
+
+extern "C" int b200bo_acq_argmin_topk(const b200bo_acq* spec, const double* Xc, int64_t m, int k,
+                                      double* best_val, int64_t* best_idx, double* topk_val,
+                                      int64_t* topk_idx, double* acq_neg) {
+    if (k < 0 || k > B200BO_MAX_TOPK) return set_err(B200BO_ERR_ARG, "k=%d out of range", k);
+    if (m <= 0) return set_err(B200BO_ERR_ARG, "m must be > 0");
+    if (spec && spec->kind == B200BO_ACQ_NONE) return set_err(B200BO_ERR_ARG, "kind NONE has no acquisition");
+    SelRecord sel[B200BO_MAX_TOPK + 1];
+    // k = 0 still needs the argmin record: run the selection with one round
+    int rc = run_host(spec, Xc, m, acq_neg, nullptr, nullptr, k > 0 ? k : 1, sel, nullptr);
+    if (rc) return rc;
+    if (best_val) *best_val = sel[0].value;
+    if (best_idx) *best_idx = sel[0].index;
+    for (int i = 0; i < k; ++i) {
+        if (topk_val) topk_val[i] = sel[1 + i].value;
+        if (topk_idx) topk_idx[i] = sel[1 + i].index;
+    }
+    return B200BO_OK;
+}

@@ -1,0 +1,319 @@
+// fit_kernels.cuh - kernel-matrix build, blocked Cholesky, triangular inverse, LML gradient.
+// Replaces (on device) the arithmetic of GaussianProcessRegressor.fit's tail and
+// log_marginal_likelihood (SK/gaussian_process/_gpr.py:349-367, :584-651).
+#pragma once
+#include "common.cuh"
+
+namespace b200bo {
+
+// ---------------------------------------------------------------------------------------
+// Xs = transform(X) / length_scale  (rows >= n are zero padding)
+// sklearn divides before differencing: cdist(X / length_scale, Y / length_scale)
+// (SK/gaussian_process/kernels.py:1716-1720).
+// ---------------------------------------------------------------------------------------
+__global__ void scale_x_kernel(const double* __restrict__ X, const double* __restrict__ ls,
+                               const int* __restrict__ xform, double* __restrict__ Xs, int n,
+                               int np, int d) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)np * d) return;
+    const int i = (int)(idx / d), j = (int)(idx % d);
+    double v = 0.0;
+    if (i < n) {
+        v = X[idx];
+        if (xform && xform[j] == B200BO_XFORM_ROUND) v = rint(v);  // np.round: half-to-even
+        v = v / ls[j];
+    }
+    Xs[idx] = v;
+}
+
+// ---------------------------------------------------------------------------------------
+// K(X,X): full symmetric np x np matrix; K_ii = const + alpha; padding = identity.
+// (SK/gaussian_process/kernels.py:1716,1740-1743 + _gpr.py:350)
+// ---------------------------------------------------------------------------------------
+__global__ void kbuild_kernel(const double* __restrict__ Xs, double* __restrict__ K, int n, int np,
+                              int d, int family, int nu, double constv, double jitter) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= np || j >= np) return;
+    double v;
+    if (i >= n || j >= n) {
+        v = (i == j) ? 1.0 : 0.0;
+    } else if (i == j) {
+        v = constv + jitter;
+    } else {
+        // pdist order: row min(i,j) first; (a-b)^2 is symmetric so the value is too
+        const double* a = Xs + (size_t)min(i, j) * d;
+        const double* b = Xs + (size_t)max(i, j) * d;
+        double r2 = 0.0;
+        for (int t = 0; t < d; ++t) {
+            const double df = a[t] - b[t];
+            r2 += df * df;
+        }
+        v = constv * cov_from_r2(r2, family, nu);
+    }
+    K[(size_t)i * np + j] = v;
+}
+
+// ---------------------------------------------------------------------------------------
+// Generic fp64 GEMM on 64x64 tiles (fit-side building block):
+//   C[m][n] = beta*C[m][n] + alpha * sum_k opA(m,k) * opB(k,n)
+//   opA(m,k) = TA ? A[k*lda+m] : A[m*lda+k];  opB(k,n) = TB ? B[n*ldb+k] : B[k*ldb+n]
+// M, N multiples of 64; K multiple of 16.  lower_only: skip tiles strictly above the diagonal.
+// kmode: 0 = full K range; 1 = k in [0, m0+64)   (A or B lower-triangular in (m,k)/(k,n) sense:
+//        caller guarantees contributions with k >= m0+64 vanish);
+//        2 = k in [n0, K)                       (contributions with k < n0 vanish)
+//        3 = k in [max(m0,n0), K)
+// Batched over blockIdx.z with element strides sA/sB/sC.
+// ---------------------------------------------------------------------------------------
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+dgemm64_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int lda,
+               long long sA, const double* __restrict__ B, int ldb, long long sB, double beta,
+               double* C, int ldc, long long sC, int lower_only, int kmode) {
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    if (lower_only && n0 > m0) return;
+    A += (long long)blockIdx.z * sA;
+    B += (long long)blockIdx.z * sB;
+    C += (long long)blockIdx.z * sC;
+    __shared__ double As[16][66];
+    __shared__ double Bs[16][66];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+    int kbeg = 0, kend = K;
+    if (kmode == 1) kend = min(K, m0 + 64);
+    if (kmode == 2) kbeg = n0;
+    if (kmode == 3) kbeg = max(m0, n0);
+
+    for (int k0 = kbeg; k0 < kend; k0 += 16) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int idx = tid + t * 256;
+            if (TA) {
+                const int m = idx & 63, kk = idx >> 6;
+                As[kk][m] = A[(size_t)(k0 + kk) * lda + m0 + m];
+            } else {
+                const int kk = idx & 15, m = idx >> 4;
+                As[kk][m] = A[(size_t)(m0 + m) * lda + k0 + kk];
+            }
+            if (TB) {
+                const int kk = idx & 15, n = idx >> 4;
+                Bs[kk][n] = B[(size_t)(n0 + n) * ldb + k0 + kk];
+            } else {
+                const int n = idx & 63, kk = idx >> 6;
+                Bs[kk][n] = B[(size_t)(k0 + kk) * ldb + n0 + n];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double* c = C + (size_t)(m0 + ty + 16 * i) * ldc + n0 + tx + 16 * j;
+            const double v = alpha * acc[i][j];
+            *c = (beta == 0.0) ? v : fma(beta, *c, v);
+        }
+}
+
+// ---------------------------------------------------------------------------------------
+// Diagonal 64x64 block: in-place Cholesky (lower) + inverse of the factor written to Dinv.
+// Single CTA, 256 threads.  info: 0 or the 1-based index of the first non-positive pivot
+// (LAPACK dpotrf convention, SP/linalg/_decomp_cholesky.py:58 raises LinAlgError on it).
+// ---------------------------------------------------------------------------------------
+constexpr int kPotrfSmemBytes = 2 * 64 * 65 * 8;
+__global__ void __launch_bounds__(256)
+potrf_diag_kernel(double* A, int ld, int j0, double* Dinv, int ldd, int* info) {
+    extern __shared__ __align__(16) double potrf_smem[];
+    double (*S)[65] = reinterpret_cast<double (*)[65]>(potrf_smem);
+    double (*V)[65] = reinterpret_cast<double (*)[65]>(potrf_smem + 64 * 65);
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < 64 * 64; idx += 256) {
+        const int r = idx >> 6, c = idx & 63;
+        S[r][c] = A[(size_t)(j0 + r) * ld + j0 + c];
+    }
+    __syncthreads();
+    for (int k = 0; k < 64; ++k) {
+        if (tid == 0) {
+            double piv = S[k][k];
+            if (!(piv > 0.0)) {
+                if (*info == 0) *info = j0 + k + 1;
+                piv = 1.0;
+            }
+            S[k][k] = sqrt(piv);
+        }
+        __syncthreads();
+        if (tid > k && tid < 64) S[tid][k] = S[tid][k] / S[k][k];
+        __syncthreads();
+        // trailing update of the lower triangle: S[i][j] -= S[i][k]*S[j][k], k < j <= i
+        for (int idx = tid; idx < 64 * 64; idx += 256) {
+            const int i = idx >> 6, j = idx & 63;
+            if (j > k && i >= j) S[i][j] = fma(-S[i][k], S[j][k], S[i][j]);
+        }
+        __syncthreads();
+    }
+    // write factor back (zero the strict upper part of the block)
+    for (int idx = tid; idx < 64 * 64; idx += 256) {
+        const int r = idx >> 6, c = idx & 63;
+        A[(size_t)(j0 + r) * ld + j0 + c] = (c <= r) ? S[r][c] : 0.0;
+    }
+    // inverse of the lower-triangular block, one column per thread (forward substitution)
+    if (tid < 64) {
+        const int c = tid;
+        for (int i = 0; i < 64; ++i) {
+            double v;
+            if (i < c) {
+                v = 0.0;
+            } else {
+                double s = (i == c) ? 1.0 : 0.0;
+                for (int k = c; k < i; ++k) s = fma(-S[i][k], V[k][c], s);
+                v = s / S[i][i];
+            }
+            V[i][c] = v;
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 64 * 64; idx += 256) {
+        const int r = idx >> 6, c = idx & 63;
+        Dinv[(size_t)r * ldd + c] = V[r][c];
+    }
+}
+
+// zero the strict upper triangle (scipy.linalg.cholesky(lower=True) returns a clean factor)
+__global__ void zero_upper_kernel(double* A, int np) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i < np && j < np && j > i) A[(size_t)i * np + j] = 0.0;
+}
+
+// out[j][i] = in[i][j]  (np multiple of 32)
+__global__ void transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int np) {
+    __shared__ double t[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y)
+        t[r][threadIdx.x] = in[(size_t)(by + r) * np + bx + threadIdx.x];
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y)
+        out[(size_t)(bx + r) * np + by + threadIdx.x] = t[threadIdx.x][r];
+}
+
+// y[i] = sum_j A[i][j] * x[j], j in [jbeg(i), jend(i)); one warp per row, fixed-order reduction.
+// tri: 0 full [0,ncols); 1 lower (j <= i); 2 upper (j >= i)
+__global__ void gemv_rows_kernel(const double* __restrict__ A, int ld, const double* __restrict__ x,
+                                 double* __restrict__ y, int nrows, int ncols, int tri) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    int jb = 0, je = ncols;
+    if (tri == 1) je = min(ncols, row + 1);
+    if (tri == 2) jb = row & ~31;
+    double s = 0.0;
+    for (int j = jb + lane; j < je; j += 32) {
+        if (tri == 2 && j < row) continue;
+        s = fma(A[(size_t)row * ld + j], x[j], s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) y[row] = s;
+}
+
+__global__ void diag_kernel(const double* __restrict__ A, int ld, double* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = A[(size_t)i * ld + i];
+}
+
+// r = y - r   (elementwise, n entries)
+__global__ void residual_kernel(const double* __restrict__ y, double* __restrict__ r, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) r[i] = y[i] - r[i];
+}
+// a += b
+__global__ void axpy1_kernel(double* __restrict__ a, const double* __restrict__ b, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] += b[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// LML gradient:  grad_p = 0.5 * sum_ij (alpha_i alpha_j - Kinv_ij) * dK_ij/dtheta_p
+// (SK/gaussian_process/_gpr.py:629-651, kernels.py:1745-1786 / :1561-1573).
+// theta order: [log const (if has_const)], log length_scale (1 or d).
+// Each CTA reduces a 16x16 patch of (i,j) pairs in a fixed order and writes its partial
+// sums to part[block][p]; the host adds the partials in index order (deterministic).
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxTheta = B200BO_MAX_DIM + 1;
+
+__global__ void __launch_bounds__(256)
+lml_grad_kernel(const double* __restrict__ Xs, const double* __restrict__ Kinv, int ldk,
+                const double* __restrict__ alphav, int n, int d, int family, int nu, double constv,
+                int has_const, int aniso, double* __restrict__ part, int ntheta) {
+    const int j = blockIdx.x * 16 + (threadIdx.x & 15);
+    const int i = blockIdx.y * 16 + (threadIdx.x >> 4);
+    __shared__ double red[256];
+    const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+    const bool valid = (i < n && j < n);
+    double w = 0.0, r2 = 0.0, kval = 0.0, gcommon = 0.0;
+    const double* a = Xs + (size_t)(valid ? i : 0) * d;
+    const double* b = Xs + (size_t)(valid ? j : 0) * d;
+    if (valid) {
+        w = alphav[i] * alphav[j] - Kinv[(size_t)i * ldk + j];
+        for (int t = 0; t < d; ++t) {
+            const double df = a[t] - b[t];
+            r2 += df * df;
+        }
+        kval = (i == j) ? 1.0 : cov_from_r2(r2, family, nu);
+        // gradient factor such that dk/dlog(l_t) = gcommon * D_t  (D_t = scaled squared diff)
+        if (family == B200BO_KERNEL_RBF || nu == B200BO_NU_INF) {
+            gcommon = kval;  // K_gradient = D * K
+        } else if (nu == B200BO_NU_25) {
+            const double tmp = sqrt(5.0 * r2);
+            gcommon = 5.0 / 3.0 * (tmp + 1.0) * exp(-tmp);
+        } else if (nu == B200BO_NU_15) {
+            gcommon = 3.0 * exp(-sqrt(3.0 * r2));
+        } else {  // nu = 0.5: K * D / sqrt(sum D), 0 where the distance is 0
+            const double den = sqrt(r2);
+            gcommon = (den != 0.0) ? kval / den : 0.0;
+        }
+    }
+    for (int p = 0; p < ntheta; ++p) {
+        double g = 0.0;
+        if (valid) {
+            if (has_const && p == 0) {
+                g = constv * kval;
+            } else if (!aniso) {
+                g = constv * gcommon * r2;
+            } else {
+                const int t = p - has_const;
+                const double df = a[t] - b[t];
+                g = constv * gcommon * (df * df);
+            }
+        }
+        red[threadIdx.x] = w * g;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) part[(size_t)bid * ntheta + p] = 0.5 * red[0];
+        __syncthreads();
+    }
+}
+
+}  // namespace b200bo

@@ -1,0 +1,413 @@
+"""B200GaussianProcessRegressor - the GP-object seam of the drop-in boundary.
+
+A subclass of sklearn's ``GaussianProcessRegressor`` (the object the reference constructs at
+R/bayes_opt/bayesian_optimization.py:124-130 and R/bayes_opt/constraint.py:72-81) whose
+``fit`` / ``predict`` / ``log_marginal_likelihood`` run on the B200 through the C ABI in
+``include/b200bo.h``.  Host logic (hyper-parameter search driver, RNG consumption, attribute
+names, error types) mirrors SK/gaussian_process/_gpr.py so the reference's callers cannot tell
+the difference; every matrix operation runs in hand-written sm_100a kernels.  There is no CPU
+fallback: unsupported kernels raise NotImplementedError, a missing CUDA library raises
+ImportError, a missing device raises B200Error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+from operator import itemgetter
+
+import numpy as np
+import scipy.optimize
+from sklearn.base import clone
+from sklearn.gaussian_process import GaussianProcessRegressor
+from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern, Product
+from sklearn.utils import check_random_state
+from sklearn.utils.optimize import _check_optimize_result
+
+from . import _lib as B
+
+
+# --------------------------------------------------------------------------------------------
+# kernel parsing: sklearn kernel object -> engine spec
+# --------------------------------------------------------------------------------------------
+class EngineKernel:
+    """What the device needs to know about a sklearn kernel, plus the theta <-> parameter map."""
+
+    def __init__(self, family, nu, const_value, length_scale, const_free, ls_free, const_first):
+        self.family = family
+        self.nu = nu
+        self.const_value = float(const_value)
+        self.length_scale = np.atleast_1d(np.asarray(length_scale, dtype=np.float64)).copy()
+        self.const_free = const_free    # ConstantKernel present and not "fixed"
+        self.ls_free = ls_free
+        self.const_first = const_first  # theta order: [const, ls] (k1=Constant) or [ls, const]
+
+    def c_spec(self):
+        self._ls_keep = np.ascontiguousarray(self.length_scale, dtype=np.float64)
+        return B.KernelSpec(self.family, self.nu, int(self._ls_keep.size), 0, self.const_value,
+                            B.as_dp(self._ls_keep))
+
+    def with_theta(self, theta):
+        """Engine kernel with the free hyper-parameters replaced by exp(theta)."""
+        theta = np.asarray(theta, dtype=np.float64)
+        k = EngineKernel(self.family, self.nu, self.const_value, self.length_scale, self.const_free,
+                         self.ls_free, self.const_first)
+        nls = self.length_scale.size if self.ls_free else 0
+        pos = 0
+        if self.const_free and self.const_first:
+            k.const_value = float(np.exp(theta[pos]))
+            pos += 1
+        if self.ls_free:
+            k.length_scale = np.exp(theta[pos:pos + nls])
+            pos += nls
+        if self.const_free and not self.const_first:
+            k.const_value = float(np.exp(theta[pos]))
+            pos += 1
+        if pos != theta.size:
+            raise ValueError("theta has the wrong number of entries")
+        return k
+
+    def select_grad(self, g_dev):
+        """Device gradient order is [const (if has_const)], ls...; reorder/select to theta order."""
+        nls = self.length_scale.size
+        off = 1 if self.const_free else 0
+        parts = []
+        g_c = g_dev[:off]
+        g_l = g_dev[off:off + nls] if self.ls_free else g_dev[:0]
+        if self.const_first:
+            parts = [g_c, g_l]
+        else:
+            parts = [g_l, g_c]
+        return np.concatenate(parts)
+
+
+_NU_CODES = {0.5: B.NU_05, 1.5: B.NU_15, 2.5: B.NU_25, np.inf: B.NU_INF}
+
+
+def _parse_base(k):
+    if isinstance(k, Matern):  # also matches WrappedKernel subclasses of Matern
+        if k.nu not in _NU_CODES:
+            raise NotImplementedError(
+                f"Matern(nu={k.nu}) is not supported by the B200 engine (nu in 0.5, 1.5, 2.5, inf)")
+        return B.KERNEL_MATERN, _NU_CODES[k.nu], k.length_scale, k.hyperparameter_length_scale.fixed
+    if isinstance(k, RBF):
+        return B.KERNEL_RBF, B.NU_INF, k.length_scale, k.hyperparameter_length_scale.fixed
+    raise NotImplementedError(
+        f"kernel {type(k).__name__} is not supported by the B200 engine; supported: Matern, RBF, "
+        "optionally multiplied by a ConstantKernel, optionally wrapped by bayes_opt wrap_kernel")
+
+
+def parse_kernel(kernel) -> EngineKernel:
+    """sklearn kernel -> EngineKernel.  Supported set: {Matern nu in (.5,1.5,2.5,inf), RBF},
+    iso/anisotropic, x ConstantKernel (either order).  Anything else: NotImplementedError."""
+    if isinstance(kernel, Product):
+        k1, k2 = kernel.k1, kernel.k2
+        if isinstance(k1, ConstantKernel) and not isinstance(k2, ConstantKernel):
+            fam, nu, ls, ls_fixed = _parse_base(k2)
+            return EngineKernel(fam, nu, k1.constant_value, ls, not k1.hyperparameter_constant_value.fixed,
+                                not ls_fixed, True)
+        if isinstance(k2, ConstantKernel) and not isinstance(k1, ConstantKernel):
+            fam, nu, ls, ls_fixed = _parse_base(k1)
+            return EngineKernel(fam, nu, k2.constant_value, ls, not k2.hyperparameter_constant_value.fixed,
+                                not ls_fixed, False)
+        raise NotImplementedError("only ConstantKernel * {Matern, RBF} products are supported")
+    fam, nu, ls, ls_fixed = _parse_base(kernel)
+    return EngineKernel(fam, nu, 1.0, ls, False, not ls_fixed, True)
+
+
+def probe_transform(kernel, d):
+    """bayes_opt's wrap_kernel (R/bayes_opt/parameter.py:457-495) stores the input transform on
+    the kernel as ``_transform``.  The engine supports per-dimension identity / np.round; the
+    transform is identified by probing it (it is an opaque callable)."""
+    t = getattr(kernel, "_transform", None)
+    if t is None and isinstance(kernel, Product):
+        t = getattr(kernel.k1, "_transform", None) or getattr(kernel.k2, "_transform", None)
+    if t is None:
+        return None
+    probe = np.array([[0.3 + j for j in range(d)], [1.7 - j for j in range(d)], [2.5 + j for j in range(d)]])
+    out = np.asarray(t(probe.copy()), dtype=float)
+    if out.shape != probe.shape:
+        raise NotImplementedError(
+            "kernel input transform changes the dimension (categorical one-hot) - not supported "
+            "by the B200 engine yet")
+    codes = np.zeros(d, dtype=np.int32)
+    for j in range(d):
+        if np.array_equal(out[:, j], probe[:, j]):
+            codes[j] = B.XFORM_IDENTITY
+        elif np.array_equal(out[:, j], np.round(probe[:, j])):
+            codes[j] = B.XFORM_ROUND
+        else:
+            raise NotImplementedError("unsupported kernel input transform on dimension %d" % j)
+    return None if not codes.any() else codes
+
+
+class _Handle:
+    """Owns one b200bo_gp*."""
+
+    def __init__(self, device):
+        self.ptr = C.c_void_p()
+        B.check(B.lib().b200bo_gp_create(C.byref(self.ptr), int(device)))
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                B.lib().b200bo_gp_destroy(self.ptr)
+                self.ptr = C.c_void_p()
+        except Exception:  # interpreter shutdown
+            pass
+
+
+class B200GaussianProcessRegressor(GaussianProcessRegressor):
+    """GaussianProcessRegressor whose numerics run on a B200 (fp64).
+
+    Same constructor as sklearn's plus ``device`` (CUDA ordinal).  ``fit`` mirrors
+    SK/gaussian_process/_gpr.py:233-368 (incl. the 1 + n_restarts_optimizer L-BFGS-B runs and the
+    exact RandomState draws at :328-333); ``predict`` mirrors :370-500 for return_std;
+    ``log_marginal_likelihood`` mirrors :541-656.
+    """
+
+    def __init__(self, kernel=None, *, alpha=1e-10, optimizer="fmin_l_bfgs_b", n_restarts_optimizer=0,
+                 normalize_y=False, copy_X_train=True, n_targets=None, random_state=None, device=0):
+        super().__init__(kernel=kernel, alpha=alpha, optimizer=optimizer,
+                         n_restarts_optimizer=n_restarts_optimizer, normalize_y=normalize_y,
+                         copy_X_train=copy_X_train, n_targets=n_targets, random_state=random_state)
+        self.device = device
+
+    # ---- device plumbing -----------------------------------------------------------------
+    def _handle(self) -> _Handle:
+        h = self.__dict__.get("_b200_handle")
+        if h is None:
+            h = _Handle(self.device)
+            self.__dict__["_b200_handle"] = h
+        return h
+
+    def __getstate__(self):
+        state = super().__getstate__() if hasattr(super(), "__getstate__") else self.__dict__.copy()
+        state = dict(state)
+        state.pop("_b200_handle", None)
+        state["_b200_device_fitted"] = False
+        return state
+
+    def _ensure_device_fit(self):
+        """After unpickling / deepcopy the device factor is gone: rebuild it at kernel_.theta."""
+        if not self.__dict__.get("_b200_device_fitted", False):
+            if not hasattr(self, "X_train_"):
+                raise B.B200Error("GP is not fitted")
+            self._device_fit(parse_kernel(self.kernel_))
+
+    def _device_fit(self, ek: EngineKernel):
+        h = self._handle()
+        X = B.c_f64(self.X_train_)
+        y = B.c_f64(self._y_raw)
+        d = X.shape[1]
+        codes = probe_transform(self.kernel_, d)
+        L = B.lib()
+        if codes is not None:
+            B.check(L.b200bo_gp_set_transform(h.ptr, codes.ctypes.data_as(C.POINTER(C.c_int32)), d))
+        else:
+            B.check(L.b200bo_gp_set_transform(h.ptr, None, d))
+        spec = ek.c_spec()
+        info = C.c_int64(0)
+        rc = L.b200bo_gp_fit(h.ptr, B.as_dp(X), B.as_dp(y), X.shape[0], d, C.byref(spec),
+                             float(self.alpha), int(bool(self.normalize_y)), C.byref(info))
+        B.check(rc)
+        self.__dict__["_b200_device_fitted"] = True
+        self.__dict__.pop("_b200_L", None)
+        self.__dict__.pop("_b200_alpha", None)
+
+    # sklearn exposes L_ and alpha_ as attributes; materialise them lazily from the device
+    @property
+    def L_(self):
+        if "_b200_L" not in self.__dict__:
+            self._ensure_device_fit()
+            n = self.X_train_.shape[0]
+            out = np.empty((n, n))
+            B.check(B.lib().b200bo_gp_get(self._handle().ptr, B.GET_L, B.as_dp(out), n * n))
+            self.__dict__["_b200_L"] = out
+        return self.__dict__["_b200_L"]
+
+    @L_.setter
+    def L_(self, v):
+        self.__dict__["_b200_L"] = v
+
+    @property
+    def alpha_(self):
+        if "_b200_alpha" not in self.__dict__:
+            self._ensure_device_fit()
+            n = self.X_train_.shape[0]
+            out = np.empty(n)
+            B.check(B.lib().b200bo_gp_get(self._handle().ptr, B.GET_ALPHA, B.as_dp(out), n))
+            self.__dict__["_b200_alpha"] = out
+        return self.__dict__["_b200_alpha"]
+
+    @alpha_.setter
+    def alpha_(self, v):
+        self.__dict__["_b200_alpha"] = v
+
+    # ---- fit -------------------------------------------------------------------------------
+    def fit(self, X, y):
+        """SK/gaussian_process/_gpr.py:233-368 with the arithmetic on the device."""
+        if self.kernel is None:
+            self.kernel_ = ConstantKernel(1.0, constant_value_bounds="fixed") * RBF(
+                1.0, length_scale_bounds="fixed")
+        else:
+            self.kernel_ = clone(self.kernel)
+        self._rng = check_random_state(self.random_state)
+        X = np.array(X, dtype=np.float64, ndmin=2, copy=True)
+        y = np.asarray(y, dtype=np.float64)
+        if y.ndim == 2 and y.shape[1] == 1:
+            y = y[:, 0]
+        if y.ndim != 1:
+            raise NotImplementedError("multi-output targets are not supported by the B200 engine")
+        if X.shape[0] != y.shape[0]:
+            raise ValueError("X and y have inconsistent numbers of samples")
+        if not (np.all(np.isfinite(X)) and np.all(np.isfinite(y))):
+            raise ValueError("Input contains NaN or infinity.")
+        if np.iterable(self.alpha):
+            raise NotImplementedError("per-sample alpha is not supported by the B200 engine")
+        self.n_features_in_ = X.shape[1]
+        ek = parse_kernel(self.kernel_)  # raises NotImplementedError for unsupported kernels
+        if ek.length_scale.size not in (1, X.shape[1]):
+            raise ValueError("Anisotropic kernel must have the same number of dimensions as data "
+                             f"({ek.length_scale.size}!={X.shape[1]})")
+
+        # normalisation statistics exactly as sklearn computes them (:275-285)
+        if self.normalize_y:
+            self._y_train_mean = np.mean(y, axis=0)
+            s = np.std(y, axis=0)
+            self._y_train_std = 1.0 if s == 0.0 else s
+            y_norm = (y - self._y_train_mean) / self._y_train_std
+        else:
+            self._y_train_mean = np.zeros(1)
+            self._y_train_std = np.ones(1)
+            y_norm = y
+        self.X_train_ = X
+        self.y_train_ = y_norm
+        self._y_raw = y.copy()
+        self.__dict__["_b200_device_fitted"] = False
+
+        if self.optimizer is not None and self.kernel_.n_dims > 0:
+            h = self._handle()
+            L = B.lib()
+            codes = probe_transform(self.kernel_, X.shape[1])
+            B.check(L.b200bo_gp_set_transform(
+                h.ptr, codes.ctypes.data_as(C.POINTER(C.c_int32)) if codes is not None else None,
+                X.shape[1]))
+            B.check(L.b200bo_gp_set_data(h.ptr, B.as_dp(X), B.as_dp(B.c_f64(y)), X.shape[0], X.shape[1],
+                                         int(bool(self.normalize_y))))
+
+            def obj_func(theta, eval_gradient=True):
+                if eval_gradient:
+                    lml, grad = self._device_lml(ek.with_theta(theta), True)
+                    return -lml, -grad
+                return -self._device_lml(ek.with_theta(theta), False)
+
+            optima = [self._constrained_optimization(obj_func, self.kernel_.theta, self.kernel_.bounds)]
+            if self.n_restarts_optimizer > 0:
+                if not np.isfinite(self.kernel_.bounds).all():
+                    raise ValueError("Multiple optimizer restarts (n_restarts_optimizer>0) "
+                                     "requires that all bounds are finite.")
+                bounds = self.kernel_.bounds
+                for _ in range(self.n_restarts_optimizer):
+                    theta_initial = self._rng.uniform(bounds[:, 0], bounds[:, 1])
+                    optima.append(self._constrained_optimization(obj_func, theta_initial, bounds))
+            lml_values = list(map(itemgetter(1), optima))
+            self.kernel_.theta = optima[np.argmin(lml_values)][0]
+            self.kernel_._check_bounds_params()
+            self.log_marginal_likelihood_value_ = -np.min(lml_values)
+            ek = parse_kernel(self.kernel_)
+            self._device_fit(ek)
+        else:
+            self._device_fit(ek)
+            self.log_marginal_likelihood_value_ = None  # computed on demand (costs one more factorisation)
+        return self
+
+    def _constrained_optimization(self, obj_func, initial_theta, bounds):
+        """SK/gaussian_process/_gpr.py:658-674."""
+        if self.optimizer == "fmin_l_bfgs_b":
+            opt_res = scipy.optimize.minimize(obj_func, initial_theta, method="L-BFGS-B", jac=True,
+                                              bounds=bounds)
+            _check_optimize_result("lbfgs", opt_res)
+            return opt_res.x, opt_res.fun
+        if callable(self.optimizer):
+            return self.optimizer(obj_func, initial_theta, bounds=bounds)
+        raise ValueError(f"Unknown optimizer {self.optimizer}.")
+
+    def _device_lml(self, ek: EngineKernel, eval_gradient):
+        h = self._handle()
+        spec = ek.c_spec()
+        lml = C.c_double(0.0)
+        ntheta_dev = (1 if ek.const_free else 0) + ek.length_scale.size
+        grad = np.zeros(ntheta_dev)
+        B.check(B.lib().b200bo_gp_lml(h.ptr, C.byref(spec), float(self.alpha), int(ek.const_free),
+                                      C.byref(lml), B.as_dp(grad) if eval_gradient else None))
+        self.__dict__["_b200_device_fitted"] = False  # factor buffers now hold this theta
+        if eval_gradient:
+            return lml.value, ek.select_grad(grad)
+        return lml.value
+
+    def log_marginal_likelihood(self, theta=None, eval_gradient=False, clone_kernel=True):
+        """SK/gaussian_process/_gpr.py:541-656."""
+        if theta is None:
+            if eval_gradient:
+                raise ValueError("Gradient can only be evaluated for theta!=None")
+            if getattr(self, "log_marginal_likelihood_value_", None) is None:
+                self.log_marginal_likelihood_value_ = self.log_marginal_likelihood(
+                    self.kernel_.theta, clone_kernel=True)
+            return self.log_marginal_likelihood_value_
+        if clone_kernel:
+            kernel = self.kernel_.clone_with_theta(theta)
+        else:
+            kernel = self.kernel_
+            kernel.theta = theta
+        h = self._handle()
+        X = B.c_f64(self.X_train_)
+        codes = probe_transform(self.kernel_, X.shape[1])
+        L = B.lib()
+        B.check(L.b200bo_gp_set_transform(
+            h.ptr, codes.ctypes.data_as(C.POINTER(C.c_int32)) if codes is not None else None, X.shape[1]))
+        B.check(L.b200bo_gp_set_data(h.ptr, B.as_dp(X), B.as_dp(B.c_f64(self._y_raw)), X.shape[0],
+                                     X.shape[1], int(bool(self.normalize_y))))
+        out = self._device_lml(parse_kernel(kernel), eval_gradient)
+        return out
+
+    # ---- predict ---------------------------------------------------------------------------
+    def predict(self, X, return_std=False, return_cov=False):
+        """SK/gaussian_process/_gpr.py:370-500 (return_std path) on the device."""
+        if return_std and return_cov:
+            raise RuntimeError("At most one of return_std or return_cov can be requested.")
+        X = np.array(X, dtype=np.float64, ndmin=2)
+        if not np.all(np.isfinite(X)):
+            raise ValueError("Input contains NaN or infinity.")
+        if not hasattr(self, "X_train_"):  # unfitted: GP prior (:417-443), no device work to do
+            if self.kernel is None:
+                kernel = ConstantKernel(1.0, constant_value_bounds="fixed") * RBF(
+                    1.0, length_scale_bounds="fixed")
+            else:
+                kernel = self.kernel
+            y_mean = np.zeros(X.shape[0])
+            if return_cov:
+                return y_mean, kernel(X)
+            if return_std:
+                return y_mean, np.sqrt(kernel.diag(X))
+            return y_mean
+        if return_cov:
+            raise NotImplementedError("predict(return_cov=True) is not on the accelerated path yet")
+        if X.shape[1] != self.X_train_.shape[1]:
+            raise ValueError(f"X has {X.shape[1]} features, but the GP was fitted with "
+                             f"{self.X_train_.shape[1]} features.")
+        self._ensure_device_fit()
+        Xc = B.c_f64(X)
+        m = Xc.shape[0]
+        mu = np.empty(m)
+        sd = np.empty(m) if return_std else None
+        nclamp = C.c_int64(0)
+        B.check(B.lib().b200bo_gp_predict(self._handle().ptr, B.as_dp(Xc), m, B.as_dp(mu),
+                                          B.as_dp(sd) if return_std else None, C.byref(nclamp)))
+        if return_std:
+            if nclamp.value > 0:
+                warnings.warn("Predicted variances smaller than 0. Setting those variances to 0.")
+            return mu, sd
+        return mu
+
+    def sample_y(self, X, n_samples=1, random_state=0):
+        raise NotImplementedError("sample_y needs return_cov; not on the accelerated path")

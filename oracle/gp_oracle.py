@@ -231,6 +231,14 @@ def base_acq(kind, mean, std, *, kappa=2.576, xi=0.01, y_max=None):
     raise ValueError(kind)
 
 
+def _frozen_norm_cdf(b, loc, scale):
+    """scipy.stats.norm(loc, scale).cdf(b): NaN unless scale > 0 (rv_continuous argcheck), else
+    ndtr((b-loc)/scale)  (SP/stats/_distn_infrastructure.py cdf, _continuous_distns.py:370)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        v = ndtr((b - loc) / scale)
+    return np.where(scale > 0, v, np.nan)
+
+
 def constraint_prob(states, lb, ub, Xc, chunk=1 << 14):
     """prod_j [Phi((ub_j-mu_j)/sd_j) - Phi((lb_j-mu_j)/sd_j)], with lb=-inf -> 0, ub=+inf -> 1
     (R/bayes_opt/constraint.py:200-221; scipy's frozen norm gives NaN for scale<=0...0/0)."""
@@ -240,8 +248,8 @@ def constraint_prob(states, lb, ub, Xc, chunk=1 << 14):
     with np.errstate(divide="ignore", invalid="ignore"):
         for j, st in enumerate(states):
             mu, sd = predict_chunked(st, Xc, chunk)
-            p_lo = ndtr((lb[j] - mu) / sd) if lb[j] != -np.inf else 0.0
-            p_hi = ndtr((ub[j] - mu) / sd) if ub[j] != np.inf else 1.0
+            p_lo = _frozen_norm_cdf(lb[j], mu, sd) if lb[j] != -np.inf else 0.0
+            p_hi = _frozen_norm_cdf(ub[j], mu, sd) if ub[j] != np.inf else 1.0
             res = res * (p_hi - p_lo)
     return res
 

@@ -1,0 +1,525 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the committed golden
+fixtures.  fp64 bar: 1e-5 relative (north_star); in practice the kernels sit near 1e-10."""
+import ctypes as C
+import pickle
+import warnings
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # the north_star bar for fp64
+
+
+@pytest.fixture(scope="module")
+def bo():
+    import bayesianoptimization_b200 as bo
+
+    return bo
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import gp_oracle
+
+    return gp_oracle
+
+
+def make_gp(bo, kernel, **kw):
+    kw.setdefault("alpha", 1e-6)
+    kw.setdefault("normalize_y", True)
+    kw.setdefault("optimizer", None)
+    return bo.B200GaussianProcessRegressor(kernel=kernel, **kw)
+
+
+def rel_err(a, b, floor=1e-300):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))
+
+
+# ------------------------------------------------------------------------------------------
+# fit: K, L, alpha_, L^-1
+# ------------------------------------------------------------------------------------------
+def test_fit_state_vs_golden(bo, golden):
+    g = golden("c2s_ei")
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=float(g["length_scale"]))).fit(g["X"], g["y"])
+    n = g["X"].shape[0]
+    from bayesianoptimization_b200 import _lib as B
+
+    K = np.empty((n, n))
+    B.check(B.lib().b200bo_gp_get(gp._handle().ptr, B.GET_K, B.as_dp(K), n * n))
+    Kref = g["K"].copy()
+    Kref[np.diag_indices(n)] += 1e-6
+    assert_allclose(K, Kref, rtol=1e-12, atol=1e-15)
+    assert_allclose(gp.L_, g["L"], rtol=1e-8, atol=1e-12)
+    assert np.all(np.triu(gp.L_, 1) == 0)
+    assert_allclose(gp.alpha_, g["alpha_"], rtol=1e-6)
+    W = np.empty((n, n))
+    B.check(B.lib().b200bo_gp_get(gp._handle().ptr, B.GET_LINV, B.as_dp(W), n * n))
+    assert_allclose(W @ g["L"], np.eye(n), atol=1e-9)
+    assert float(gp._y_train_mean) == pytest.approx(float(g["y_mean"]), rel=1e-14)
+    assert float(gp._y_train_std) == pytest.approx(float(g["y_std"]), rel=1e-14)
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 127, 129, 200, 257, 700])
+def test_factor_padding_and_ragged_sizes(bo, O, n):
+    rs = np.random.RandomState(n)
+    d = 3
+    X = rs.uniform(size=(n, d))
+    y = np.sin(3 * X.sum(1)) + 0.05 * rs.randn(n)
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=0.5)).fit(X, y)
+    st = O.fit_fixed(X, y, length_scale=0.5)
+    assert_allclose(gp.L_, st.L, rtol=1e-7, atol=1e-11)
+    xt = rs.uniform(size=(300, d))
+    mu, sd = gp.predict(xt, return_std=True)
+    mu0, sd0 = O.predict(st, xt)
+    assert_allclose(mu, mu0, rtol=RTOL, atol=1e-9)
+    assert_allclose(sd, sd0, rtol=RTOL, atol=1e-8)
+
+
+# ------------------------------------------------------------------------------------------
+# predict + acquisition vs golden (reference outputs)
+# ------------------------------------------------------------------------------------------
+def test_c2s_predict_and_acq_vs_golden(bo, golden):
+    g = golden("c2s_ei")
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=float(g["length_scale"]))).fit(g["X"], g["y"])
+    mu, sd = gp.predict(g["xt"], return_std=True)
+    assert_allclose(mu, g["mu"], rtol=RTOL, atol=1e-10)
+    assert_allclose(sd, g["sd"], rtol=RTOL, atol=1e-10)
+    assert_allclose(gp.predict(g["xt"]), g["mu"], rtol=RTOL, atol=1e-10)
+    for cls, key, kw in [
+        (bo.ExpectedImprovement, "acq_ei", dict(xi=float(g["xi"]))),
+        (bo.ProbabilityOfImprovement, "acq_poi", dict(xi=float(g["xi"]))),
+        (bo.UpperConfidenceBound, "acq_ucb", dict(kappa=float(g["kappa"]))),
+    ]:
+        a = cls(**kw)
+        if hasattr(a, "y_max"):
+            a.y_max = float(g["y_max"])
+        f = a._get_acq(gp=gp)
+        ys = f(g["xt"])
+        assert_allclose(ys, g[key], rtol=RTOL, atol=1e-14)
+        if key == "acq_ei":
+            idx, val, top = f.argmin_topk(g["xt"], 10)
+            assert idx == int(g["argmin"])
+            assert val == ys[idx]
+            assert list(top) == list(g["top10"])
+            # single-row calls (what L-BFGS-B does) agree bit-for-bit with the batch
+            for i in (0, 17, 4095):
+                assert f(g["xt"][i])[0] == ys[i]
+
+
+def test_c1_readme_ucb_vs_golden(bo, golden):
+    g = golden("c1_readme_ucb")
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=float(g["length_scale"]))).fit(g["X"], g["y"])
+    assert_allclose(gp.L_, g["L"], rtol=1e-8, atol=1e-12)
+    mu, sd = gp.predict(g["xt"], return_std=True)
+    assert_allclose(mu, g["mu"], rtol=RTOL, atol=1e-9)
+    assert_allclose(sd, g["sd"], rtol=RTOL, atol=1e-8)
+    f = bo.UpperConfidenceBound(kappa=float(g["kappa"]))._get_acq(gp=gp)
+    ys = f(g["xt"])
+    assert_allclose(ys, g["acq"], rtol=RTOL, atol=1e-8)
+    assert int(np.argmin(ys)) == int(np.argmin(g["acq"]))
+    assert_allclose([f(g["xt"][i])[0] for i in range(16)], g["acq_single"], rtol=RTOL, atol=1e-8)
+
+
+def test_near_duplicate_candidates(bo, golden):
+    g = golden("c2s_ei")
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=float(g["length_scale"]))).fit(g["X"], g["y"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mu, sd = gp.predict(g["xe"], return_std=True)
+    assert_allclose(mu, g["mu_e"], rtol=RTOL, atol=1e-8)
+    # sigma at the jitter floor is a difference of O(1) numbers; LAPACK itself only has
+    # absolute accuracy there
+    assert_allclose(sd, g["sd_e"], rtol=1e-3, atol=2e-7)
+
+
+KERNELS = {
+    "m05": (lambda: Matern(nu=0.5, length_scale=0.6)),
+    "m15": (lambda: Matern(nu=1.5, length_scale=0.6)),
+    "rbf": (lambda: RBF(length_scale=0.6)),
+    "m25aniso": (lambda: Matern(nu=2.5, length_scale=[0.3, 0.6, 1.2, 2.4])),
+    "crbf": (lambda: ConstantKernel(2.0) * RBF(length_scale=0.8)),
+    "cm25": (lambda: ConstantKernel(0.5) * Matern(nu=2.5, length_scale=0.5)),
+}
+
+
+@pytest.mark.parametrize("tag", sorted(KERNELS))
+def test_kernel_families_vs_golden(bo, golden, tag):
+    g = golden("kernels_small")
+    gp = make_gp(bo, KERNELS[tag]()).fit(g["X"], g["y"])
+    assert_allclose(gp.L_, g[f"{tag}_L"], rtol=1e-8, atol=1e-12)
+    mu, sd = gp.predict(g["xt"], return_std=True)
+    assert_allclose(mu, g[f"{tag}_mu"], rtol=RTOL, atol=1e-9)
+    assert_allclose(sd, g[f"{tag}_sd"], rtol=RTOL, atol=1e-9)
+    lml, grad = gp.log_marginal_likelihood(gp.kernel_.theta, eval_gradient=True)
+    assert lml == pytest.approx(float(g[f"{tag}_lml"]), rel=1e-8)
+    assert_allclose(grad, g[f"{tag}_lml_grad"], rtol=1e-5, atol=1e-6)
+    # the factor buffers now hold another theta; predict must transparently re-factorise
+    mu2 = gp.predict(g["xt"])
+    assert_allclose(mu2, mu, rtol=0, atol=0)
+
+
+def test_lml_and_gradient_vs_golden(bo, golden):
+    g = golden("c2s_ei")
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=0.7)).fit(g["X"], g["y"])
+    for t, v, gr in zip(g["thetas"], g["lml"], g["lml_grad"]):
+        lml, grad = gp.log_marginal_likelihood(np.array([t]), eval_gradient=True)
+        assert lml == pytest.approx(float(v), rel=1e-8, abs=1e-8)
+        assert grad[0] == pytest.approx(float(gr), rel=1e-5, abs=1e-5)
+        assert gp.log_marginal_likelihood(np.array([t])) == pytest.approx(float(v), rel=1e-8, abs=1e-8)
+
+
+def test_constrained_acquisition_vs_golden(bo, golden):
+    g = golden("c4s_constrained")
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=float(g["ls"]))).fit(g["X"], g["y"])
+    cm = bo.ConstraintModel(None, g["lb"], g["ub"])
+    for m, l in zip(cm.model, g["ls_c"]):
+        m.set_params(kernel=Matern(nu=2.5, length_scale=float(l)), optimizer=None)
+    cm.fit(g["X"], g["c"])
+    assert_allclose(cm.predict(g["xt"]), g["p"], rtol=RTOL, atol=1e-12)
+    assert_allclose(cm.approx(g["xt"]), g["approx"], rtol=RTOL, atol=1e-9)
+    for cls, key in [(bo.ProbabilityOfImprovement, "acq_poi"), (bo.ExpectedImprovement, "acq_ei")]:
+        a = cls(xi=float(g["xi"]))
+        a.y_max = float(g["y_max"])
+        ys = a._get_acq(gp=gp, constraint=cm)(g["xt"])
+        assert_allclose(ys, g[key], rtol=RTOL, atol=1e-13)
+    cm1 = bo.ConstraintModel(None, -0.5, 0.5)
+    cm1.model[0].set_params(kernel=Matern(nu=2.5, length_scale=0.5), optimizer=None)
+    cm1.fit(g["X"], g["c"][:, 1])
+    assert_allclose(cm1.predict(g["xt"]), g["p1"], rtol=RTOL, atol=1e-12)
+    a = bo.ExpectedImprovement(xi=float(g["xi"]))
+    a.y_max = float(g["y_max"])
+    ys1 = a._get_acq(gp=gp, constraint=cm1)(g["xt"])
+    # J=1 fused == (-EI) * p1
+    ei = a._get_acq(gp=gp)(g["xt"])
+    assert_allclose(ys1, ei * g["p1"], rtol=RTOL, atol=1e-13)
+
+
+# ------------------------------------------------------------------------------------------
+# hyper-parameter fit (device LML driven by host L-BFGS-B): two-tier parity
+# ------------------------------------------------------------------------------------------
+def test_full_fit_vs_golden(bo, golden):
+    g = golden("fit_full_small")
+    rs = np.random.RandomState(3)
+    gp = bo.B200GaussianProcessRegressor(kernel=Matern(nu=2.5), alpha=1e-6, normalize_y=True,
+                                         n_restarts_optimizer=5, random_state=rs)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gp.fit(g["X"], g["y"])
+    # the shared RandomState advanced exactly as sklearn's fit advances it
+    assert_allclose(rs.uniform(size=3), g["next_uniform"], rtol=0, atol=0)
+    assert gp.log_marginal_likelihood_value_ == pytest.approx(float(g["lml"]), rel=1e-7)
+    assert_allclose(gp.kernel_.theta, g["theta"], rtol=1e-4, atol=1e-4)
+    mu, sd = gp.predict(g["xt"], return_std=True)
+    assert_allclose(mu, g["mu"], rtol=1e-3, atol=1e-4)  # theta* only matches to optimiser tolerance
+    assert_allclose(sd, g["sd"], rtol=1e-3, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------
+# larger sizes vs the oracle
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,m", [(1000, 8, 5000), (1024, 8, 4096), (2048, 16, 3000)])
+def test_midsize_vs_oracle(bo, O, n, d, m):
+    rs = np.random.RandomState(5)
+    X = rs.uniform(size=(n, d))
+    y = np.sin(X.sum(1)) + 0.1 * rs.randn(n)
+    xt = rs.uniform(size=(m, d))
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=0.7)).fit(X, y)
+    st = O.fit_fixed(X, y, length_scale=0.7)
+    assert_allclose(gp.L_, st.L, rtol=1e-6, atol=1e-10)
+    a = bo.ExpectedImprovement(xi=0.01)
+    a.y_max = float(y.max())
+    f = a._get_acq(gp=gp)
+    ys = f(xt)
+    ref = O.acq_closure(st, O.ACQ_EI, xi=0.01, y_max=float(y.max()))(xt)
+    assert_allclose(ys, ref, rtol=RTOL, atol=1e-14)
+    idx, val, top = f.argmin_topk(xt, 10)
+    i0, v0, t0 = O.argmin_topk(ref, 10)
+    assert idx == i0 and list(top) == list(t0)
+    mu, sd = gp.predict(xt, return_std=True)
+    mu0, sd0 = O.predict(st, xt)
+    assert_allclose(mu, mu0, rtol=RTOL, atol=1e-10)
+    assert_allclose(sd, sd0, rtol=RTOL, atol=1e-10)
+
+
+def test_c3_full_size_vs_oracle_and_properties(bo, O):
+    """BASELINE config 3 sizes (N=4096, d=16): direct oracle comparison on 4096 candidates plus
+    size-independent properties (linearity of mu in y, variance independent of y, interpolation
+    at training points, batch == single-row)."""
+    n, d, m = 4096, 16, 4096
+    rs = np.random.RandomState(0)
+    X = rs.uniform(size=(n, d))
+    y = np.sin(X.sum(1)) + 0.1 * rs.randn(n)
+    xt = rs.uniform(size=(m, d))
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=0.7)).fit(X, y)
+    st = O.fit_fixed(X, y, length_scale=0.7)
+    a = bo.ExpectedImprovement(xi=0.01)
+    a.y_max = float(y.max())
+    f = a._get_acq(gp=gp)
+    ys = f(xt)
+    ref = O.acq_closure(st, O.ACQ_EI, xi=0.01, y_max=float(y.max()))(xt)
+    assert_allclose(ys, ref, rtol=RTOL, atol=1e-14)
+    assert int(np.argmin(ys)) == int(np.argmin(ref))
+    mu, sd = gp.predict(xt, return_std=True)
+    mu0, sd0 = O.predict(st, xt)
+    assert_allclose(mu, mu0, rtol=RTOL, atol=1e-10)
+    assert_allclose(sd, sd0, rtol=RTOL, atol=1e-10)
+    # interpolation: at training points |mu - y| is tiny compared with the data scale
+    mu_tr, sd_tr = gp.predict(X[:512], return_std=True)
+    assert np.max(np.abs(mu_tr - y[:512])) < 1e-2
+    assert np.max(sd_tr) < 5e-2
+    # linearity in y (normalize_y=False), variance independent of y
+    y2 = np.cos(2 * X.sum(1))
+    g1 = make_gp(bo, Matern(nu=2.5, length_scale=0.7), normalize_y=False).fit(X, y)
+    m1, s1 = g1.predict(xt[:1024], return_std=True)
+    g2 = make_gp(bo, Matern(nu=2.5, length_scale=0.7), normalize_y=False).fit(X, y2)
+    m2, s2 = g2.predict(xt[:1024], return_std=True)
+    g3 = make_gp(bo, Matern(nu=2.5, length_scale=0.7), normalize_y=False).fit(X, y + y2)
+    m3, s3 = g3.predict(xt[:1024], return_std=True)
+    assert_allclose(m1 + m2, m3, rtol=1e-8, atol=1e-9)
+    assert np.array_equal(s1, s2) and np.array_equal(s1, s3)
+    # batch == single row, and run-to-run bit reproducibility
+    assert f(xt[7])[0] == ys[7]
+    assert np.array_equal(f(xt), ys)
+
+
+# ------------------------------------------------------------------------------------------
+# selection semantics, edge cases, errors
+# ------------------------------------------------------------------------------------------
+def test_selection_semantics_ties(bo):
+    """argmin / top-k selection: ties -> lowest index (np.argmin / stable argsort order)."""
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=0.5)).fit(np.random.RandomState(0).rand(5, 2), np.arange(5.0))
+    rs = np.random.RandomState(3)
+    xt = rs.rand(777, 2)
+    f = bo.UpperConfidenceBound(kappa=1.0)._get_acq(gp=gp)
+    ys = f(xt)
+    idx, val, top = f.argmin_topk(xt, 20)
+    assert idx == int(np.argmin(ys)) and val == ys.min()
+    assert list(top) == list(np.argsort(ys, kind="stable")[:20])
+    # duplicated candidates -> exact ties -> lowest index first
+    xt2 = np.vstack([xt[:100], xt[:100]])
+    ys2 = f(xt2)
+    idx2, _, top2 = f.argmin_topk(xt2, 8)
+    assert idx2 == int(np.argmin(ys2))
+    assert list(top2) == list(np.argsort(ys2, kind="stable")[:8])
+    # fewer candidates than seeds requested
+    idx3, _, top3 = f.argmin_topk(xt[:3], 10)
+    assert idx3 == int(np.argmin(ys[:3])) and list(top3) == list(np.argsort(ys[:3], kind="stable"))
+
+
+def test_selection_nan_semantics(bo):
+    """NaN acquisition values: np.argmin returns the FIRST NaN; np.argsort puts NaNs last."""
+    X = np.array([[0.1], [0.5], [0.9]])
+    y = np.array([0.0, 1.0, 0.5])
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=0.3), alpha=1e-12, normalize_y=False).fit(X, y)
+    a = bo.ExpectedImprovement(xi=0.0)
+    a.y_max = 1.0
+    f = a._get_acq(gp=gp)
+    rs = np.random.RandomState(0)
+    xt = np.vstack([rs.rand(50, 1), X, rs.rand(50, 1), X])
+    ys = f(xt)
+    idx, val, top = f.argmin_topk(xt, 12)
+    assert idx == int(np.argmin(ys))
+    assert list(top) == list(np.argsort(ys, kind="stable")[:12])
+
+
+def test_sigma_zero_nan_semantics(bo):
+    """EI with sigma == 0: a*Phi(+-inf) + 0*phi -> a or 0; a == 0 and sigma == 0 -> NaN, and NaN is
+    np.argmin's minimum (SURVEY section 7 'EI/PoI edge semantics')."""
+    X = np.array([[0.1], [0.5], [0.9]])
+    y = np.array([0.0, 1.0, 0.5])
+    # alpha=0 -> exact interpolation -> clamped variance 0 at training points
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=0.3), alpha=1e-12, normalize_y=False).fit(X, y)
+    a = bo.ExpectedImprovement(xi=0.0)
+    a.y_max = 1.0
+    f = a._get_acq(gp=gp)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mu, sd = gp.predict(X, return_std=True)
+    ys = f(X)
+    for i in range(3):
+        if sd[i] == 0.0:
+            aa = mu[i] - 1.0
+            expect = np.nan if aa == 0 else (-aa if aa > 0 else 0.0)
+            assert (np.isnan(ys[i]) and np.isnan(expect)) or ys[i] == pytest.approx(expect, abs=1e-12)
+
+
+def test_not_positive_definite_raises_linalgerror(bo):
+    X = np.vstack([np.full((1, 2), 0.5)] * 3 + [np.array([[0.1, 0.2]])])
+    y = np.array([1.0, 2.0, 3.0, 4.0])
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=1.0), alpha=0.0)
+    with pytest.raises(np.linalg.LinAlgError):
+        gp.fit(X, y)
+
+
+def test_unsupported_kernel_raises(bo):
+    from sklearn.gaussian_process.kernels import RationalQuadratic
+
+    gp = make_gp(bo, RationalQuadratic())
+    with pytest.raises(NotImplementedError):
+        gp.fit(np.random.rand(5, 2), np.random.rand(5))
+    gp = make_gp(bo, Matern(nu=1.0))
+    with pytest.raises(NotImplementedError):
+        gp.fit(np.random.rand(5, 2), np.random.rand(5))
+
+
+def test_prior_predict_unfitted(bo):
+    gp = make_gp(bo, Matern(nu=2.5))
+    mu, sd = gp.predict(np.random.rand(7, 3), return_std=True)
+    assert np.all(mu == 0) and np.all(sd == 1)
+
+
+def test_pickle_roundtrip_refits_on_device(bo, golden):
+    g = golden("c2s_ei")
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=0.7)).fit(g["X"], g["y"])
+    mu = gp.predict(g["xt"][:256])
+    gp2 = pickle.loads(pickle.dumps(gp))
+    assert np.array_equal(gp2.predict(g["xt"][:256]), mu)
+
+
+def test_round_transform_for_int_parameters(bo, O):
+    """wrap_kernel with np.round on one dimension (R/bayes_opt/parameter.py:308-320, :484-487)."""
+    rs = np.random.RandomState(2)
+    X = np.column_stack([rs.uniform(0, 1, 80), np.round(rs.uniform(0, 10, 80))])
+    y = np.sin(X[:, 0] * 3) + 0.1 * X[:, 1]
+
+    def transform(v):
+        v = np.atleast_2d(v).astype(float).copy()
+        v[:, 1] = np.round(v[:, 1])
+        return v
+
+    k = Matern(nu=2.5, length_scale=0.8)
+    k._transform = transform  # what wrap_kernel stores (parameter.py:494)
+    gp = make_gp(bo, k).fit(X, y)
+    xt = np.column_stack([rs.uniform(0, 1, 500), rs.uniform(0, 10, 500)])
+    mu, sd = gp.predict(xt, return_std=True)
+    st = O.fit_fixed(transform(X), y, length_scale=0.8)
+    mu0, sd0 = O.predict(st, transform(xt))
+    assert_allclose(mu, mu0, rtol=RTOL, atol=1e-10)
+    assert_allclose(sd, sd0, rtol=RTOL, atol=1e-9)
+
+
+def test_c_abi_direct_calls(bo, golden):
+    """Raw ctypes calls against include/b200bo.h (no Python classes in between)."""
+    from bayesianoptimization_b200 import _lib as B
+
+    L = B.lib()
+    g = golden("c2s_ei")
+    h = C.c_void_p()
+    assert L.b200bo_gp_create(C.byref(h), 0) == 0
+    ls = np.array([float(g["length_scale"])])
+    spec = B.KernelSpec(B.KERNEL_MATERN, B.NU_25, 1, 0, 1.0, B.as_dp(ls))
+    X, y, xt = B.c_f64(g["X"]), B.c_f64(g["y"]), B.c_f64(g["xt"])
+    info = C.c_int64()
+    assert L.b200bo_gp_fit(h, B.as_dp(X), B.as_dp(y), X.shape[0], X.shape[1], C.byref(spec), 1e-6, 1,
+                           C.byref(info)) == 0
+    assert L.b200bo_gp_n(h) == X.shape[0] and L.b200bo_gp_dim(h) == X.shape[1]
+    mu, sd = np.empty(len(xt)), np.empty(len(xt))
+    ncl = C.c_int64()
+    assert L.b200bo_gp_predict(h, B.as_dp(xt), len(xt), B.as_dp(mu), B.as_dp(sd), C.byref(ncl)) == 0
+    assert_allclose(mu, g["mu"], rtol=RTOL, atol=1e-10)
+    assert_allclose(sd, g["sd"], rtol=RTOL, atol=1e-10)
+    acq = B.AcqSpec()
+    acq.kind, acq.n_gps, acq.xi, acq.y_max = B.ACQ_EI, 1, float(g["xi"]), float(g["y_max"])
+    acq.gps[0] = h.value
+    out = np.empty(len(xt))
+    bv, bi = C.c_double(), C.c_int64()
+    tv, ti = np.empty(10), np.empty(10, dtype=np.int64)
+    assert L.b200bo_acq_argmin_topk(C.byref(acq), B.as_dp(xt), len(xt), 10, C.byref(bv), C.byref(bi),
+                                    B.as_dp(tv), ti.ctypes.data_as(C.POINTER(C.c_int64)), B.as_dp(out)) == 0
+    assert_allclose(out, g["acq_ei"], rtol=RTOL, atol=1e-14)
+    assert bi.value == int(g["argmin"]) and list(ti) == list(g["top10"])
+    ms = C.c_float()
+    assert L.b200bo_last_kernel_ms(C.byref(ms)) == 0 and ms.value > 0
+    # argument errors come back as codes + message, never a crash
+    assert L.b200bo_gp_predict(h, None, 5, B.as_dp(mu), None, None) == B.ERR_ARG
+    assert b"candidates" in L.b200bo_last_error()
+    L.b200bo_gp_destroy(h)
+
+
+def test_device_resident_entry_point(bo, golden):
+    """b200bo_acq_eval_dev with torch-owned device buffers on a non-default stream."""
+    import torch
+
+    from bayesianoptimization_b200 import _lib as B
+
+    g = golden("c2s_ei")
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=0.7)).fit(g["X"], g["y"])
+    a = bo.ExpectedImprovement(xi=float(g["xi"]))
+    a.y_max = float(g["y_max"])
+    f = a._get_acq(gp=gp)
+    xt = torch.from_numpy(g["xt"]).cuda()
+    out = torch.empty(xt.shape[0], dtype=torch.float64, device="cuda")
+    sel = torch.zeros((11, 2), dtype=torch.int64, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        B.check(B.lib().b200bo_acq_eval_dev(C.byref(f.spec), xt.data_ptr(), xt.shape[0], out.data_ptr(),
+                                            None, None, 10, sel.data_ptr(), 1000, s.cuda_stream))
+    s.synchronize()
+    assert_allclose(out.cpu().numpy(), g["acq_ei"], rtol=RTOL, atol=1e-14)
+    idx = sel[:, 1].cpu().numpy()
+    assert idx[0] == int(g["argmin"]) + 1000
+    assert list(idx[1:] - 1000) == list(g["top10"])
+    vals = sel[:, 0].cpu().numpy().view(np.float64)
+    assert vals[0] == g["acq_ei"].min() or abs(vals[0] - g["acq_ei"].min()) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------
+# end-to-end suggest()
+# ------------------------------------------------------------------------------------------
+def test_suggest_end_to_end_readme(bo, golden):
+    """Full suggest() (fit with 5 restarts + 10k candidates + 10 L-BFGS-B refinements) from the
+    reference's RNG state: end-to-end tier - same point to optimiser tolerance."""
+    g = golden("c1_readme_ucb")
+    space = bo.TargetSpace(None, {"x": (2, 4), "y": (-3, 3)})
+    for x, t in zip(g["X"], g["y"]):
+        space.register(x, t)
+    rs = np.random.RandomState()
+    rs.set_state(("MT19937", g["rs_keys"], int(g["rs_pos"]), 0, 0.0))
+    gp = bo.B200GaussianProcessRegressor(kernel=Matern(nu=2.5), alpha=1e-6, normalize_y=True,
+                                         n_restarts_optimizer=5, random_state=rs)
+    acq = bo.UpperConfidenceBound(kappa=float(g["kappa"]))
+    x1 = acq.suggest(gp, space, random_state=rs)
+    assert_allclose(x1, g["suggestion"], rtol=1e-3, atol=1e-3)
+    # determinism pin of the reference's save/load tests: same state -> identical suggestion
+    rs.set_state(("MT19937", g["rs_keys"], int(g["rs_pos"]), 0, 0.0))
+    acq2 = bo.UpperConfidenceBound(kappa=float(g["kappa"]))
+    x2 = acq2.suggest(gp, space, random_state=rs)
+    assert np.array_equal(x1, x2)
+
+
+def test_constant_liar_vs_golden(bo, golden):
+    g = golden("constant_liar_small")
+    space = bo.TargetSpace(lambda x, y: -((x - 3) ** 2) - (y - 1) ** 2, {"x": (1, 4), "y": (0, 3.0)})
+    for x, t in zip(g["X"], g["y"]):
+        space.register(x, t)
+    gp = bo.B200GaussianProcessRegressor(kernel=Matern(nu=2.5), alpha=1e-6, normalize_y=True,
+                                         n_restarts_optimizer=5, random_state=np.random.RandomState(0))
+    cl = bo.ConstantLiar(bo.UpperConfidenceBound(kappa=2.576), strategy="max")
+    rng = np.random.RandomState(5)
+    sug = [cl.suggest(gp=gp, target_space=space, random_state=rng) for _ in range(4)]
+    assert_allclose(np.array(sug), g["suggestions"], rtol=2e-3, atol=2e-3)
+    assert len(cl.dummies) == 4
+
+
+def test_constrained_suggest_runs_and_respects_errors(bo):
+    from bayesianoptimization_b200.exception import ConstraintNotSupportedError, TargetSpaceEmptyError
+
+    cm = bo.ConstraintModel(lambda x, y: x + y, -np.inf, 4.0)
+    space = bo.TargetSpace(lambda x, y: -((x - 3) ** 2) - (y - 1) ** 2, {"x": (1, 4), "y": (0, 3.0)},
+                           constraint=cm)
+    gp = bo.B200GaussianProcessRegressor(kernel=Matern(nu=2.5), alpha=1e-6, normalize_y=True,
+                                         n_restarts_optimizer=2, random_state=np.random.RandomState(0))
+    ei = bo.ExpectedImprovement(xi=0.01)
+    with pytest.raises(TargetSpaceEmptyError):
+        ei.suggest(gp, space, random_state=np.random.RandomState(1))
+    rs = np.random.RandomState(0)
+    for _ in range(8):
+        space.probe(space.random_sample(random_state=rs))
+    x = ei.suggest(gp, space, n_random=2000, n_smart=3, random_state=rs)
+    assert x.shape == (2,) and np.all(x >= space.bounds[:, 0]) and np.all(x <= space.bounds[:, 1])
+    with pytest.raises(ConstraintNotSupportedError):
+        bo.UpperConfidenceBound().suggest(gp, space, random_state=rs)

