@@ -7,20 +7,11 @@ from scipy.special import ndtr
 from sklearn.gaussian_process.kernels import Matern
 
 from .gpr import B200GaussianProcessRegressor
+from .kernels import wrap_kernel
 
 
 def _wrap(kernel, transform):
-    """Use the reference's wrap_kernel when it is installed (keeps pickles interchangeable);
-    identity transforms need no wrapper."""
-    if transform is None:
-        return kernel
-    try:
-        from bayes_opt.parameter import wrap_kernel  # type: ignore
-
-        return wrap_kernel(kernel, transform)
-    except Exception:
-        probe = np.array([[0.3, 1.7]])
-        return kernel  # float-only spaces: transform is the identity (space.kernel_transform)
+    return kernel if transform is None else wrap_kernel(kernel, transform)
 
 
 class ConstraintModel:

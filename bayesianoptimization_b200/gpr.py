@@ -24,6 +24,7 @@ from sklearn.utils import check_random_state
 from sklearn.utils.optimize import _check_optimize_result
 
 from . import _lib as B
+from .kernels import find_transform
 
 
 # --------------------------------------------------------------------------------------------
@@ -118,9 +119,9 @@ def probe_transform(kernel, d):
     """bayes_opt's wrap_kernel (R/bayes_opt/parameter.py:457-495) stores the input transform on
     the kernel as ``_transform``.  The engine supports per-dimension identity / np.round; the
     transform is identified by probing it (it is an opaque callable)."""
-    t = getattr(kernel, "_transform", None)
+    t = find_transform(kernel)
     if t is None and isinstance(kernel, Product):
-        t = getattr(kernel.k1, "_transform", None) or getattr(kernel.k2, "_transform", None)
+        t = find_transform(kernel.k1) or find_transform(kernel.k2)
     if t is None:
         return None
     probe = np.array([[0.3 + j for j in range(d)], [1.7 - j for j in range(d)], [2.5 + j for j in range(d)]])

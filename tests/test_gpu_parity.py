@@ -391,9 +391,9 @@ def test_round_transform_for_int_parameters(bo, O):
         v[:, 1] = np.round(v[:, 1])
         return v
 
-    k = Matern(nu=2.5, length_scale=0.8)
-    k._transform = transform  # what wrap_kernel stores (parameter.py:494)
-    gp = make_gp(bo, k).fit(X, y)
+    from bayesianoptimization_b200.kernels import wrap_kernel
+
+    gp = make_gp(bo, wrap_kernel(Matern(nu=2.5, length_scale=0.8), transform)).fit(X, y)
     xt = np.column_stack([rs.uniform(0, 1, 500), rs.uniform(0, 10, 500)])
     mu, sd = gp.predict(xt, return_std=True)
     st = O.fit_fixed(transform(X), y, length_scale=0.8)

@@ -96,6 +96,10 @@ def test_kernel_parsing(bo):
 def test_transform_probe(bo):
     from bayesianoptimization_b200.gpr import probe_transform
 
+    from sklearn.base import clone
+
+    from bayesianoptimization_b200.kernels import wrap_kernel
+
     k = Matern(nu=2.5)
     assert probe_transform(k, 3) is None
     k._transform = lambda v: np.atleast_2d(v)
@@ -108,6 +112,11 @@ def test_transform_probe(bo):
 
     k._transform = rnd
     assert list(probe_transform(k, 3)) == [0, 0, 1]
+    # sklearn.base.clone drops instance attributes: the transform must be found in the closure
+    wk = clone(wrap_kernel(Matern(nu=2.5, length_scale=0.4), rnd))
+    assert not hasattr(wk, "_transform") and wk.length_scale == 0.4
+    assert list(probe_transform(wk, 3)) == [0, 0, 1]
+    assert np.allclose(wk(np.array([[0.1, 0.2, 1.4]]), np.array([[0.1, 0.2, 0.6]])), 1.0)
     k._transform = lambda v: np.hstack([np.atleast_2d(v), np.atleast_2d(v)])
     with pytest.raises(NotImplementedError):
         probe_transform(k, 3)

@@ -10,7 +10,7 @@ echo "pytest exit $?"; tail -n 40 gpurun_out/pytest_gpu.log
 echo "== smoke"
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -n 5 gpurun_out/smoke.log
 echo "== microbench"
-timeout 120 gpurun_out/microbench > gpurun_out/microbench.json 2>&1; cat gpurun_out/microbench.json
+timeout 120 tools/_bin/microbench > tools/_bin/microbench.json 2>&1; cat tools/_bin/microbench.json
 if [ "$mode" = "quick" ]; then exit 0; fi
 echo "== bench"
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; cat gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err

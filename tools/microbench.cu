@@ -1,6 +1,6 @@
 // microbench.cu - measured fp64 ceilings on this B200 (roofline denominators that
 // MEASURED_PEAKS.json does not carry): DFMA issue rate and DMMA (mma.sync f64) rate.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/microbench tools/microbench.cu
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/_bin/microbench tools/microbench.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 
