@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -80,6 +81,9 @@ struct b200bo_gp {
     DevBuf X, Xs, y, K, L, W, WT, T, alphav, v1, v2, ls, xf, info, part;
     // predict-side scratch (used when this handle is gps[0] of a call)
     DevBuf pscratch, xc, out_acq, out_mu, out_sd, sel, clamp;
+    // small-batch path scratch (per GP) + work-unit tables (rebuilt when np changes)
+    DevBuf s_ksm, s_partial, s_mupart, s_unit, s_rb;
+    int s_np = 0, s_nunits = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
@@ -119,8 +123,14 @@ extern "C" int b200bo_gp_create(b200bo_gp** out, int device) {
     gp->sm_count = prop.multiProcessorCount;
     CU(cudaEventCreate(&gp->ev0));
     CU(cudaEventCreate(&gp->ev1));
-    CU(cudaFuncSetAttribute(predict_acq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            kPredictSmemBytes));
+    CU(cudaFuncSetAttribute(predict_acq_kernel<PREDICT_IMPL_DFMA, false>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDfma));
+    CU(cudaFuncSetAttribute(predict_acq_kernel<PREDICT_IMPL_DFMA, true>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDfma));
+    CU(cudaFuncSetAttribute(predict_acq_kernel<PREDICT_IMPL_DMMA, false>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDmma));
+    CU(cudaFuncSetAttribute(predict_acq_kernel<PREDICT_IMPL_DMMA, true>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDmma));
     CU(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             kPotrfSmemBytes));
     *out = gp;
@@ -133,7 +143,7 @@ extern "C" void b200bo_gp_destroy(b200bo_gp* gp) {
     DevBuf* bufs[] = {&gp->X, &gp->Xs, &gp->y, &gp->K, &gp->L, &gp->W, &gp->WT, &gp->T,
                       &gp->alphav, &gp->v1, &gp->v2, &gp->ls, &gp->xf, &gp->info, &gp->part,
                       &gp->pscratch, &gp->xc, &gp->out_acq, &gp->out_mu, &gp->out_sd, &gp->sel,
-                      &gp->clamp};
+                      &gp->clamp, &gp->s_ksm, &gp->s_partial, &gp->s_mupart, &gp->s_unit, &gp->s_rb};
     for (DevBuf* b : bufs) b->release();
     if (gp->ev0) cudaEventDestroy(gp->ev0);
     if (gp->ev1) cudaEventDestroy(gp->ev1);
@@ -477,6 +487,54 @@ extern "C" int b200bo_gp_get(b200bo_gp* gp, int what, double* out, int64_t len) 
 // ---------------------------------------------------------------------------------------
 // predict / acquisition
 // ---------------------------------------------------------------------------------------
+// small-batch path: work-unit tables + scratch for one GP
+static int ensure_small(b200bo_gp* gp) {
+    const int np = gp->np;
+    if (gp->s_np == np) return B200BO_OK;
+    std::vector<int2> units, rbs;
+    const int nrb = np / SROWS;
+    for (int i = 0; i < nrb; ++i) {
+        const int K = (i + 1) * SROWS;
+        const int nj = (K + SKCH - 1) / SKCH;
+        rbs.push_back(make_int2((int)units.size(), nj));
+        for (int j = 0; j < nj; ++j) units.push_back(make_int2(i, j));
+    }
+    int rc;
+    if ((rc = gp->s_unit.reserve(sizeof(int2) * units.size()))) return rc;
+    if ((rc = gp->s_rb.reserve(sizeof(int2) * rbs.size()))) return rc;
+    if ((rc = gp->s_ksm.reserve(sizeof(double) * (size_t)np * SMC))) return rc;
+    if ((rc = gp->s_partial.reserve(sizeof(double) * units.size() * SROWS * SMC))) return rc;
+    if ((rc = gp->s_mupart.reserve(sizeof(double) * (size_t)(np / 128) * SMC))) return rc;
+    CU(cudaMemcpy(gp->s_unit.p, units.data(), sizeof(int2) * units.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(gp->s_rb.p, rbs.data(), sizeof(int2) * rbs.size(), cudaMemcpyHostToDevice));
+    gp->s_np = np;
+    gp->s_nunits = (int)units.size();
+    return B200BO_OK;
+}
+
+// Cost model (microseconds, measured orders of magnitude on B200) choosing between the tiled
+// persistent kernel and the small-batch path.  B200BO_SMALL_PATH=0/1 forces one of them.
+static bool use_small_path(long long m, int np_max, int n_gps, int sm_count) {
+    const char* e = getenv("B200BO_SMALL_PATH");
+    if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
+    if (m <= 0) return false;
+    const double x = (np_max / 4096.0) * (np_max / 4096.0);
+    const double passes = (double)((m + SMC - 1) / SMC);
+    const double tiles = (double)((m + PBN - 1) / PBN);
+    const double t_small = passes * (15.0 + 60.0 * x) * n_gps;
+    const double t_big = std::ceil(tiles / sm_count) * (10.0 + 9000.0 * x) * n_gps;
+    return t_small < t_big;
+}
+
+// GEMM inner-loop variant of the fused predict kernel: "dmma" (mma.sync m8n8k4 f64, default) or
+// "dfma" (8x8 register tiles).  Both are exact fp64 with fixed-order reductions; the environment
+// variable B200BO_PREDICT_IMPL selects one for A/B measurements.
+static int predict_impl() {
+    const char* e = getenv("B200BO_PREDICT_IMPL");
+    if (e && (e[0] == 'd' || e[0] == 'D') && (e[1] == 'f' || e[1] == 'F')) return PREDICT_IMPL_DFMA;
+    return PREDICT_IMPL_DMMA;
+}
+
 static int check_spec(const b200bo_acq* spec) {
     if (!spec) return set_err(B200BO_ERR_ARG, "spec is NULL");
     if (spec->n_gps < 1 || spec->n_gps > B200BO_MAX_GPS)
@@ -550,12 +608,53 @@ extern "C" int b200bo_acq_eval_dev(const b200bo_acq* spec, const double* d_Xc, i
     CU(cudaMemsetAsync(g0->clamp.p, 0, sizeof(unsigned long long), stream));
     const long long ntiles = (m + PBN - 1) / PBN;
     int grid = (int)(ntiles < g0->sm_count ? ntiles : g0->sm_count);
-    if (grid > 0) {
+    if (grid > 0 && use_small_path(m, np_max, spec->n_gps, g0->sm_count)) {
+        SmallParams S;
+        memset(&S, 0, sizeof(S));
+        S.P = P;
+        for (int g = 0; g < spec->n_gps; ++g) {
+            b200bo_gp* gp = spec->gps[g];
+            if ((rc = ensure_small(gp))) return rc;
+            S.sg[g].W = gp->W.as<double>();
+            S.sg[g].ksm = gp->s_ksm.as<double>();
+            S.sg[g].partial = gp->s_partial.as<double>();
+            S.sg[g].mu_part = gp->s_mupart.as<double>();
+            S.sg[g].unit_tab = gp->s_unit.as<int2>();
+            S.sg[g].rb_tab = gp->s_rb.as<int2>();
+        }
+        CU(cudaEventRecord(g0->ev0, stream));
+        for (long long c0 = 0; c0 < m; c0 += SMC) {
+            S.c0 = c0;
+            S.mc = (int)((m - c0) < SMC ? (m - c0) : SMC);
+            for (int g = 0; g < spec->n_gps; ++g) {
+                small_kstar_kernel<<<spec->gps[g]->np / 128, 128, 0, stream>>>(S, g);
+                small_trsv_kernel<<<spec->gps[g]->s_nunits, 256, 0, stream>>>(S, g);
+                LAUNCHED();
+                LAUNCHED();
+            }
+            small_finish_kernel<<<1, 1024, 0, stream>>>(S);
+            LAUNCHED();
+        }
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(g0->ev1, stream));
+        g_last_timed = g0;
+    } else if (grid > 0) {
         P.scratch_stride = (long long)np_max * PBN;
         if ((rc = g0->pscratch.reserve(sizeof(double) * (size_t)P.scratch_stride * g0->sm_count))) return rc;
         P.scratch = g0->pscratch.as<double>();
         CU(cudaEventRecord(g0->ev0, stream));
-        predict_acq_kernel<<<grid, PNT, kPredictSmemBytes, stream>>>(P);
+        const bool dreg = P.d <= kPredictMaxDimRegs;
+        if (predict_impl() == PREDICT_IMPL_DMMA) {
+            if (dreg)
+                predict_acq_kernel<PREDICT_IMPL_DMMA, true><<<grid, PNT, kPredictSmemBytesDmma, stream>>>(P);
+            else
+                predict_acq_kernel<PREDICT_IMPL_DMMA, false><<<grid, PNT, kPredictSmemBytesDmma, stream>>>(P);
+        } else {
+            if (dreg)
+                predict_acq_kernel<PREDICT_IMPL_DFMA, true><<<grid, PNT, kPredictSmemBytesDfma, stream>>>(P);
+            else
+                predict_acq_kernel<PREDICT_IMPL_DFMA, false><<<grid, PNT, kPredictSmemBytesDfma, stream>>>(P);
+        }
         LAUNCHED();
         CU(cudaGetLastError());
         CU(cudaEventRecord(g0->ev1, stream));

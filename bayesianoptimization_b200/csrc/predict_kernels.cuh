@@ -50,8 +50,341 @@ struct PredictParams {
 };
 
 constexpr int PBM = 128, PBN = 128, PBK = 16, PSTAGES = 3, PNT = 256;
-constexpr int kPredictSmemBytes = PSTAGES * PBK * (PBM + PBN) * 8;  // 98304
+// smem row stride (doubles) of the A/B k-tiles.  DFMA variant: dense rows (conflict-free 16-byte
+// fragment loads).  DMMA variant: +4 doubles: an LDS.64 is served per half-warp (4 k-rows x 4
+// columns of an m8n8k4 fragment); a row stride of 264 words = 8 (mod 32) puts the four k-rows of
+// each half-warp on disjoint bank octets -> 2 wavefronts per request, the minimum for 256 bytes.
+constexpr int PSTR_DFMA = 128, PSTR_DMMA = 132;
+constexpr int kPredictSmemBytesDfma = PSTAGES * PBK * 2 * PSTR_DFMA * 8;  // 98304
+constexpr int PBK_DMMA = 32;  // k-tile of the DMMA variant (one CTA barrier per 32 k)
+constexpr int kPredictSmemBytesDmma = PSTAGES * PBK_DMMA * 2 * PSTR_DMMA * 8;  // 202752
+constexpr int kPredictMaxDimRegs = 16;  // candidates held in registers when d <= 16
 
+enum { PREDICT_IMPL_DFMA = 0, PREDICT_IMPL_DMMA = 1 };
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ---- per-candidate epilogue shared by the tiled and the small-batch kernels ---------------------
+// mu_n: K* alpha_ (normalised units); colsq: sum_i V_i^2.  g = 0: target GP -> base acquisition;
+// g >= 1: constraint GP -> probability factor.  The last GP writes -base * prod.
+__device__ __forceinline__ void candidate_epilogue(const PredictParams& P, const GpDev& G, int g,
+                                                   double mu_n, double colsq, long long gi,
+                                                   double& base_neg, double& prod) {
+    const double mean = G.y_std * mu_n + G.y_mean;
+    double var = G.constv - colsq;
+    if (var < 0.0) {
+        var = 0.0;
+        if (P.clamp_count && gi < P.m) atomicAdd(P.clamp_count, 1ull);
+    }
+    const double sd = sqrt(var * (G.y_std * G.y_std));
+    if (g == 0) {
+        double base = 0.0;
+        if (P.acq_kind == B200BO_ACQ_UCB) {
+            base = mean + P.kappa * sd;
+        } else if (P.acq_kind == B200BO_ACQ_EI) {
+            const double a = mean - P.y_max - P.xi;
+            const double z = a / sd;
+            base = a * ndtr(z) + sd * norm_pdf(z);
+        } else if (P.acq_kind == B200BO_ACQ_POI) {
+            const double z = (mean - P.y_max - P.xi) / sd;
+            base = ndtr(z);
+        }
+        base_neg = -1.0 * base;
+        prod = 1.0;
+        if (gi < P.m) {
+            if (P.mu_out) P.mu_out[gi] = mean;
+            if (P.sd_out) P.sd_out[gi] = sd;
+        }
+    } else {
+        const double p_lo = (G.lb == -CUDART_INF) ? 0.0 : norm_cdf_loc_scale(G.lb, mean, sd);
+        const double p_hi = (G.ub == CUDART_INF) ? 1.0 : norm_cdf_loc_scale(G.ub, mean, sd);
+        // constraint.py:208 (J=1: result = p_hi - p_lo) / :219 (result *= ...)
+        prod = (g == 1) ? (p_hi - p_lo) : prod * (p_hi - p_lo);
+    }
+    if (g == P.n_gps - 1 && P.acq_out && gi < P.m)
+        P.acq_out[gi] = (P.n_gps > 1) ? base_neg * prod : base_neg;
+}
+
+// ---- phase A: K*^T tile (np x 128) into the CTA's scratch + K* alpha_ ---------------------------
+// DREG: candidate coordinates in registers (d <= 16, zero padded) - one 16-byte uniform load of the
+// training row serves two dimensions; generic path keeps the candidate tile in shared memory.
+template <bool DREG>
+__device__ __forceinline__ void predict_phase_a(const PredictParams& P, const GpDev& G, long long c0,
+                                                double* __restrict__ Ks, double* xc_s,
+                                                double (*mu_s)[PBN]) {
+    const int tid = threadIdx.x;
+    const int d = P.d, np = G.np;
+    for (int idx = tid; idx < PBN * d; idx += PNT) {
+        const int c = idx / d, j = idx - c * d;
+        const long long gi = c0 + c;
+        double v = 0.0;
+        if (gi < P.m) {
+            v = P.Xc[gi * d + j];
+            if (G.xform && G.xform[j] == B200BO_XFORM_ROUND) v = rint(v);
+            v = v / G.ls[j];
+        }
+        xc_s[j * PBN + c] = v;
+    }
+    __syncthreads();
+    const int c = tid & (PBN - 1), half = tid >> 7;
+    double mu_acc = 0.0;
+    if (DREG) {
+        double xc[kPredictMaxDimRegs];
+#pragma unroll
+        for (int j = 0; j < kPredictMaxDimRegs; ++j) xc[j] = (j < d) ? xc_s[j * PBN + c] : 0.0;
+        const int dp = (d + 1) & ~1;  // Xs rows are read two dimensions at a time
+        constexpr int R = 8;  // rows per iteration: 8 independent distance chains per thread
+        for (int n0 = half * R; n0 < np; n0 += 2 * R) {
+            double r2[R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) r2[q] = 0.0;
+            const double* x0 = G.Xs + (size_t)n0 * d;
+            if ((d & 1) == 0) {
+#pragma unroll
+                for (int j = 0; j < kPredictMaxDimRegs; j += 2) {
+                    if (j < dp) {
+#pragma unroll
+                        for (int q = 0; q < R; ++q) {
+                            const double2 xv = __ldg(reinterpret_cast<const double2*>(x0 + q * d + j));
+                            const double d0 = xc[j] - xv.x, d1 = xc[j + 1] - xv.y;
+                            r2[q] = fma(d0, d0, r2[q]);
+                            r2[q] = fma(d1, d1, r2[q]);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kPredictMaxDimRegs; ++j) {
+                    if (j < d) {
+#pragma unroll
+                        for (int q = 0; q < R; ++q) {
+                            const double df = xc[j] - __ldg(x0 + q * d + j);
+                            r2[q] = fma(df, df, r2[q]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int n = n0 + q;
+                double kv = 0.0;
+                if (n < G.n) kv = G.constv * cov_from_r2(r2[q], G.family, G.nu);
+                Ks[(size_t)n * PBN + c] = kv;
+                mu_acc = fma(__ldg(G.alphav + n), kv, mu_acc);
+            }
+        }
+    } else {
+        for (int n0 = half * 4; n0 < np; n0 += 8) {
+            double r2[4] = {0.0, 0.0, 0.0, 0.0};
+            const double* x0 = G.Xs + (size_t)n0 * d;
+            for (int j = 0; j < d; ++j) {
+                const double xv = xc_s[j * PBN + c];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double df = xv - __ldg(x0 + q * d + j);
+                    r2[q] = fma(df, df, r2[q]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int n = n0 + q;
+                double kv = 0.0;
+                if (n < G.n) kv = G.constv * cov_from_r2(r2[q], G.family, G.nu);
+                Ks[(size_t)n * PBN + c] = kv;
+                mu_acc = fma(__ldg(G.alphav + n), kv, mu_acc);
+            }
+        }
+    }
+    mu_s[half][c] = mu_acc;
+    __threadfence_block();
+    __syncthreads();
+}
+
+// stage loader shared by both GEMM variants: BK k-rows x 128 doubles of LinvT and of K*
+template <int STR, int BK>
+__device__ __forceinline__ void predict_load_stage(double* as, double* bs, const double* Ag,
+                                                   const double* Bg, int np) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int t = 0; t < BK / 4; ++t) {
+        const int q = tid + t * PNT;
+        const int kk = q >> 6, m2 = (q & 63) * 2;
+        cp_async16_cg(as + kk * STR + m2, Ag + (size_t)kk * np + m2);
+        cp_async16_cg(bs + kk * STR + m2, Bg + kk * PBN + m2);
+    }
+}
+
+// ---- phase B (DFMA): 8x8 register tiles; returns per-column sums of V^2 in red[16][PBN] -------
+__device__ __forceinline__ void predict_phase_b_dfma(const GpDev& G, const double* __restrict__ Ks,
+                                                     double* smem) {
+    constexpr int STR = PSTR_DFMA, BK = PBK;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int np = G.np;
+    double* As = smem;
+    double* Bs = smem + PSTAGES * BK * STR;
+    double csq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) csq[j] = 0.0;
+    const int nb = np / PBM;
+    for (int ib = 0; ib < nb; ++ib) {
+        double acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+        const int nks = (ib + 1) * (PBM / BK);
+        const double* Abase = G.linvT + (size_t)ib * PBM;
+#pragma unroll
+        for (int s = 0; s < PSTAGES - 1; ++s) {
+            if (s < nks)
+                predict_load_stage<STR, BK>(As + s * BK * STR, Bs + s * BK * STR,
+                                            Abase + (size_t)(s * BK) * np, Ks + (size_t)(s * BK) * PBN, np);
+            cp_async_commit();
+        }
+        for (int ks = 0; ks < nks; ++ks) {
+            cp_async_wait<PSTAGES - 2>();
+            __syncthreads();
+            const int nxt = ks + PSTAGES - 1;
+            if (nxt < nks)
+                predict_load_stage<STR, BK>(As + (nxt % PSTAGES) * BK * STR, Bs + (nxt % PSTAGES) * BK * STR,
+                                            Abase + (size_t)(nxt * BK) * np, Ks + (size_t)(nxt * BK) * PBN, np);
+            cp_async_commit();
+            const double* as = As + (ks % PSTAGES) * BK * STR;
+            const double* bs = Bs + (ks % PSTAGES) * BK * STR;
+#pragma unroll
+            for (int kk = 0; kk < PBK; ++kk) {
+                double a[8], b[8];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const double2 t = *reinterpret_cast<const double2*>(as + kk * STR + p * 32 + ty * 2);
+                    a[2 * p] = t.x;
+                    a[2 * p + 1] = t.y;
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const double2 t = *reinterpret_cast<const double2*>(bs + kk * STR + p * 32 + tx * 2);
+                    b[2 * p] = t.x;
+                    b[2 * p + 1] = t.y;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s = fma(acc[i][j], acc[i][j], s);
+            csq[j] += s;
+        }
+    }
+    double* red = smem;  // [16][PBN]
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        red[ty * PBN + p * 32 + tx * 2] = csq[2 * p];
+        red[ty * PBN + p * 32 + tx * 2 + 1] = csq[2 * p + 1];
+    }
+    __syncthreads();
+}
+
+// ---- phase B (DMMA): mma.sync m8n8k4 f64; warp tile 32(m) x 64(n); red[4][PBN] -----------------
+__device__ __forceinline__ void predict_phase_b_dmma(const GpDev& G, const double* __restrict__ Ks,
+                                                     double* smem) {
+    constexpr int STR = PSTR_DMMA, BK = PBK_DMMA;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int np = G.np;
+    double* As = smem;
+    double* Bs = smem + PSTAGES * BK * STR;
+    double csq[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) csq[j][0] = csq[j][1] = 0.0;
+    const int nb = np / PBM;
+    for (int ib = 0; ib < nb; ++ib) {
+        double acc[4][8][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        const int nks = (ib + 1) * (PBM / BK);
+        const double* Abase = G.linvT + (size_t)ib * PBM;
+#pragma unroll
+        for (int s = 0; s < PSTAGES - 1; ++s) {
+            if (s < nks)
+                predict_load_stage<STR, BK>(As + s * BK * STR, Bs + s * BK * STR,
+                                            Abase + (size_t)(s * BK) * np, Ks + (size_t)(s * BK) * PBN, np);
+            cp_async_commit();
+        }
+        for (int ks = 0; ks < nks; ++ks) {
+            cp_async_wait<PSTAGES - 2>();
+            __syncthreads();
+            const int nxt = ks + PSTAGES - 1;
+            if (nxt < nks)
+                predict_load_stage<STR, BK>(As + (nxt % PSTAGES) * BK * STR, Bs + (nxt % PSTAGES) * BK * STR,
+                                            Abase + (size_t)(nxt * BK) * np, Ks + (size_t)(nxt * BK) * PBN, np);
+            cp_async_commit();
+            const double* as = As + (ks % PSTAGES) * BK * STR + wm * 32 + g;
+            const double* bs = Bs + (ks % PSTAGES) * BK * STR + wn * 64 + g;
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 4; ++k4) {
+                double a[4], b[8];
+                const int krow = (k4 * 4 + t4) * STR;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = as[krow + i * 8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b[j] = bs[krow + j * 8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                s0 = fma(acc[i][j][0], acc[i][j][0], s0);
+                s1 = fma(acc[i][j][1], acc[i][j][1], s1);
+            }
+            csq[j][0] += s0;
+            csq[j][1] += s1;
+        }
+    }
+    // rows of one m8 fragment live in lanes with equal (lane & 3): butterfly over lane bits 2..4
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            double v = csq[j][e];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            csq[j][e] = v;
+        }
+    double* red = smem;  // [4][PBN]
+    if (g == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            red[wm * PBN + wn * 64 + j * 8 + t4 * 2] = csq[j][0];
+            red[wm * PBN + wn * 64 + j * 8 + t4 * 2 + 1] = csq[j][1];
+        }
+    }
+    __syncthreads();
+}
+
+template <int IMPL, bool DREG>
 __global__ void __launch_bounds__(PNT, 1) predict_acq_kernel(const PredictParams P) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double mu_s[2][PBN];
@@ -59,191 +392,181 @@ __global__ void __launch_bounds__(PNT, 1) predict_acq_kernel(const PredictParams
     __shared__ double prod_s[PBN];
 
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
-    const int d = P.d;
     double* Ks = P.scratch + (long long)blockIdx.x * P.scratch_stride;
     const long long ntiles = (P.m + PBN - 1) / PBN;
-
-    double* As = smem;                           // [PSTAGES][PBK][PBM]
-    double* Bs = smem + PSTAGES * PBK * PBM;     // [PSTAGES][PBK][PBN]
-    double* xc_s = smem;                         // phase A: [d][PBN]
-    double* red = smem;                          // reduction: [16][PBN]
+    constexpr int NRED = (IMPL == PREDICT_IMPL_DMMA) ? 4 : 16;
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long c0 = tile * PBN;
         for (int g = 0; g < P.n_gps; ++g) {
             const GpDev& G = P.gp[g];
-            const int np = G.np;
-            // ---------------- phase A: K*^T tile + K* alpha_ -------------------------------
-            for (int idx = tid; idx < PBN * d; idx += PNT) {
-                const int c = idx / d, j = idx - c * d;
-                const long long gi = c0 + c;
-                double v = 0.0;
-                if (gi < P.m) {
-                    v = P.Xc[gi * d + j];
-                    if (G.xform && G.xform[j] == B200BO_XFORM_ROUND) v = rint(v);
-                    v = v / G.ls[j];
-                }
-                xc_s[j * PBN + c] = v;
-            }
-            __syncthreads();
-            {
-                const int c = tid & (PBN - 1), half = tid >> 7;
-                double mu_acc = 0.0;
-                for (int n0 = half * 4; n0 < np; n0 += 8) {
-                    double r2[4] = {0.0, 0.0, 0.0, 0.0};
-                    const double* x0 = G.Xs + (size_t)n0 * d;
-                    for (int j = 0; j < d; ++j) {
-                        const double xv = xc_s[j * PBN + c];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const double df = xv - __ldg(x0 + q * d + j);
-                            r2[q] = fma(df, df, r2[q]);
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int n = n0 + q;
-                        double kv = 0.0;
-                        if (n < G.n) kv = G.constv * cov_from_r2(r2[q], G.family, G.nu);
-                        Ks[(size_t)n * PBN + c] = kv;
-                        mu_acc = fma(__ldg(G.alphav + n), kv, mu_acc);
-                    }
-                }
-                mu_s[half][c] = mu_acc;
-            }
-            __threadfence_block();
-            __syncthreads();
-
-            // ---------------- phase B: V = Linv K*^T, column sums of V^2 --------------------
-            double csq[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) csq[j] = 0.0;
-            const int nb = np / PBM;
-            for (int ib = 0; ib < nb; ++ib) {
-                double acc[8][8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
-                const int nks = (ib + 1) * (PBM / PBK);
-                const double* Abase = G.linvT + (size_t)ib * PBM;
-
-                auto load_stage = [&](int stage, int ks) {
-                    const double* Ag = Abase + (size_t)(ks * PBK) * np;
-                    const double* Bg = Ks + (size_t)(ks * PBK) * PBN;
-                    double* as = As + stage * PBK * PBM;
-                    double* bs = Bs + stage * PBK * PBN;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const int q = tid + t * PNT;
-                        const int kk = q >> 6, m2 = (q & 63) * 2;
-                        cp_async16_cg(as + kk * PBM + m2, Ag + (size_t)kk * np + m2);
-                        cp_async16_cg(bs + kk * PBN + m2, Bg + kk * PBN + m2);
-                    }
-                };
-
-#pragma unroll
-                for (int s = 0; s < PSTAGES - 1; ++s) {
-                    if (s < nks) load_stage(s, s);
-                    cp_async_commit();
-                }
-                for (int ks = 0; ks < nks; ++ks) {
-                    cp_async_wait<PSTAGES - 2>();
-                    __syncthreads();
-                    const int nxt = ks + PSTAGES - 1;
-                    if (nxt < nks) load_stage(nxt % PSTAGES, nxt);
-                    cp_async_commit();
-                    const double* as = As + (ks % PSTAGES) * PBK * PBM;
-                    const double* bs = Bs + (ks % PSTAGES) * PBK * PBN;
-#pragma unroll
-                    for (int kk = 0; kk < PBK; ++kk) {
-                        double a[8], b[8];
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) {
-                            const double2 t =
-                                *reinterpret_cast<const double2*>(as + kk * PBM + p * 32 + ty * 2);
-                            a[2 * p] = t.x;
-                            a[2 * p + 1] = t.y;
-                        }
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) {
-                            const double2 t =
-                                *reinterpret_cast<const double2*>(bs + kk * PBN + p * 32 + tx * 2);
-                            b[2 * p] = t.x;
-                            b[2 * p + 1] = t.y;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
-                    }
-                }
-                cp_async_wait<0>();
-                __syncthreads();
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) s = fma(acc[i][j], acc[i][j], s);
-                    csq[j] += s;
-                }
-            }
-            // reduce csq over the 16 row-threads sharing each column (fixed order)
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                red[ty * PBN + p * 32 + tx * 2] = csq[2 * p];
-                red[ty * PBN + p * 32 + tx * 2 + 1] = csq[2 * p + 1];
-            }
-            __syncthreads();
+            predict_phase_a<DREG>(P, G, c0, Ks, smem, mu_s);
+            if (IMPL == PREDICT_IMPL_DMMA)
+                predict_phase_b_dmma(G, Ks, smem);
+            else
+                predict_phase_b_dfma(G, Ks, smem);
+            const double* red = smem;
 
             // ---------------- phase C: per-candidate epilogue --------------------------------
             if (tid < PBN) {
                 const int c = tid;
-                const long long gi = c0 + c;
                 double colsq = 0.0;
 #pragma unroll
-                for (int r = 0; r < 16; ++r) colsq += red[r * PBN + c];
-                const double mu_n = mu_s[0][c] + mu_s[1][c];
-                const double mean = G.y_std * mu_n + G.y_mean;
-                double var = G.constv - colsq;
-                if (var < 0.0) {
-                    var = 0.0;
-                    if (P.clamp_count && gi < P.m) atomicAdd(P.clamp_count, 1ull);
-                }
-                const double sd = sqrt(var * (G.y_std * G.y_std));
-                if (g == 0) {
-                    double base = 0.0;
-                    if (P.acq_kind == B200BO_ACQ_UCB) {
-                        base = mean + P.kappa * sd;
-                    } else if (P.acq_kind == B200BO_ACQ_EI) {
-                        const double a = mean - P.y_max - P.xi;
-                        const double z = a / sd;
-                        base = a * ndtr(z) + sd * norm_pdf(z);
-                    } else if (P.acq_kind == B200BO_ACQ_POI) {
-                        const double z = (mean - P.y_max - P.xi) / sd;
-                        base = ndtr(z);
-                    }
-                    base_s[c] = -1.0 * base;
-                    prod_s[c] = 1.0;
-                    if (gi < P.m) {
-                        if (P.mu_out) P.mu_out[gi] = mean;
-                        if (P.sd_out) P.sd_out[gi] = sd;
-                    }
-                } else {
-                    const double p_lo =
-                        (G.lb == -CUDART_INF) ? 0.0 : norm_cdf_loc_scale(G.lb, mean, sd);
-                    const double p_hi =
-                        (G.ub == CUDART_INF) ? 1.0 : norm_cdf_loc_scale(G.ub, mean, sd);
-                    // constraint.py:208 (J=1: result = p_hi - p_lo) / :219 (result *= ...)
-                    prod_s[c] = (g == 1) ? (p_hi - p_lo) : prod_s[c] * (p_hi - p_lo);
-                }
-                if (g == P.n_gps - 1 && P.acq_out && gi < P.m) {
-                    P.acq_out[gi] = (P.n_gps > 1) ? base_s[c] * prod_s[c] : base_s[c];
-                }
+                for (int r = 0; r < NRED; ++r) colsq += red[r * PBN + c];
+                candidate_epilogue(P, G, g, mu_s[0][c] + mu_s[1][c], colsq, c0 + c, base_s[c], prod_s[c]);
             }
             __syncthreads();
         }
+    }
+}
+
+// =======================================================================================
+// Small-batch path (m <= a few hundred candidates: the single-row / finite-difference-stencil
+// calls L-BFGS-B makes, R/bayes_opt/acquisition.py:366).  The tiled kernel would run one
+// 128-wide tile on one SM; here the triangular product V = Linv K*^T for up to 32 candidates is
+// spread over the whole GPU as fixed-size work units (64 rows x <=512 k), with fixed-order
+// partial sums (deterministic).  Three launches per pass of 32 candidates and per GP:
+//   small_kstar_kernel  K*[k][c] (+ per-block partials of K* alpha_)
+//   small_trsv_kernel   partial V for each (row-block, k-chunk) unit
+//   small_finish_kernel sum units, square, reduce rows, epilogue (all GPs)
+// =======================================================================================
+constexpr int SMC = 32;      // candidates per pass
+constexpr int SROWS = 64;    // rows per unit
+constexpr int SKCH = 512;    // k per unit
+constexpr int SKT = 32;      // k sub-tile staged in smem
+constexpr int SWSTR = SKT + 2;
+
+struct SmallGp {
+    const double* W;        // [np][np] Linv row-major
+    double* ksm;            // [np][SMC]
+    double* partial;        // [nunits][SROWS][SMC]
+    double* mu_part;        // [np/128][SMC]
+    const int2* unit_tab;   // [nunits] (row-block, k-chunk)
+    const int2* rb_tab;     // [np/SROWS] (first unit, number of units)
+};
+
+struct SmallParams {
+    PredictParams P;
+    SmallGp sg[B200BO_MAX_GPS];
+    long long c0;  // first candidate of this pass
+    int mc;        // candidates in this pass (<= SMC)
+};
+
+__global__ void __launch_bounds__(128)
+small_kstar_kernel(const SmallParams S, int g) {
+    const GpDev& G = S.P.gp[g];
+    const SmallGp& Q = S.sg[g];
+    __shared__ double xc_s[SMC * B200BO_MAX_DIM];
+    __shared__ double wsum[4][SMC];
+    const int tid = threadIdx.x, d = S.P.d;
+    for (int idx = tid; idx < SMC * d; idx += 128) {
+        const int c = idx / d, j = idx - c * d;
+        double v = 0.0;
+        if (c < S.mc) {
+            v = S.P.Xc[(S.c0 + c) * d + j];
+            if (G.xform && G.xform[j] == B200BO_XFORM_ROUND) v = rint(v);
+            v = v / G.ls[j];
+        }
+        xc_s[idx] = v;
+    }
+    __syncthreads();
+    const int n = blockIdx.x * 128 + tid;
+    const double* xr = G.Xs + (size_t)n * d;
+    const double an = G.alphav[n];
+    for (int c = 0; c < SMC; ++c) {
+        double kv = 0.0;
+        if (c < S.mc && n < G.n) {
+            double r2 = 0.0;
+            for (int j = 0; j < d; ++j) {
+                const double df = xc_s[c * d + j] - xr[j];
+                r2 = fma(df, df, r2);
+            }
+            kv = G.constv * cov_from_r2(r2, G.family, G.nu);
+        }
+        Q.ksm[(size_t)n * SMC + c] = kv;
+        double t = an * kv;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if ((tid & 31) == 0) wsum[tid >> 5][c] = t;
+    }
+    __syncthreads();
+    if (tid < SMC)
+        Q.mu_part[(size_t)blockIdx.x * SMC + tid] = ((wsum[0][tid] + wsum[1][tid]) + wsum[2][tid]) + wsum[3][tid];
+}
+
+__global__ void __launch_bounds__(256)
+small_trsv_kernel(const SmallParams S, int g) {
+    const GpDev& G = S.P.gp[g];
+    const SmallGp& Q = S.sg[g];
+    __shared__ __align__(16) double Wt[SROWS * SWSTR];
+    __shared__ __align__(16) double Kt[SKT * SMC];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int2 u = Q.unit_tab[blockIdx.x];
+    const int r0 = u.x * SROWS;
+    const int kbeg = u.y * SKCH;
+    const int kend = min(kbeg + SKCH, r0 + SROWS);
+    const int np = G.np;
+    double acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+    for (int k0 = kbeg; k0 < kend; k0 += SKT) {
+        for (int idx = tid; idx < SROWS * SKT; idx += 256) {
+            const int r = idx / SKT, kk = idx % SKT;
+            Wt[r * SWSTR + kk] = Q.W[(size_t)(r0 + r) * np + k0 + kk];
+        }
+        for (int idx = tid; idx < SKT * SMC; idx += 256) Kt[idx] = Q.ksm[(size_t)k0 * SMC + idx];
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < SKT; kk += 2) {
+            const double k0v = Kt[kk * SMC + lane], k1v = Kt[(kk + 1) * SMC + lane];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const double2 w = *reinterpret_cast<const double2*>(&Wt[(warp * 8 + q) * SWSTR + kk]);
+                acc[q] = fma(w.x, k0v, acc[q]);
+                acc[q] = fma(w.y, k1v, acc[q]);
+            }
+        }
+        __syncthreads();
+    }
+    double* out = Q.partial + (size_t)blockIdx.x * SROWS * SMC;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) out[(warp * 8 + q) * SMC + lane] = acc[q];
+}
+
+__global__ void __launch_bounds__(1024)
+small_finish_kernel(const SmallParams S) {
+    __shared__ double red[32][SMC + 1];
+    __shared__ double colsq_s[B200BO_MAX_GPS][SMC];
+    __shared__ double mu_s[B200BO_MAX_GPS][SMC];
+    const int tid = threadIdx.x, c = tid & 31, rg = tid >> 5;
+    for (int g = 0; g < S.P.n_gps; ++g) {
+        const GpDev& G = S.P.gp[g];
+        const SmallGp& Q = S.sg[g];
+        double s = 0.0;
+        for (int row = rg; row < G.np; row += 32) {
+            const int2 rb = Q.rb_tab[row / SROWS];
+            const int r = row % SROWS;
+            double v = 0.0;
+            for (int j = 0; j < rb.y; ++j) v += Q.partial[((size_t)(rb.x + j) * SROWS + r) * SMC + c];
+            s = fma(v, v, s);
+        }
+        red[rg][c] = s;
+        __syncthreads();
+        if (rg == 0) {
+            double t = 0.0;
+            for (int r = 0; r < 32; ++r) t += red[r][c];
+            colsq_s[g][c] = t;
+            double m = 0.0;
+            const int nb = G.np / 128;
+            for (int b = 0; b < nb; ++b) m += Q.mu_part[(size_t)b * SMC + c];
+            mu_s[g][c] = m;
+        }
+        __syncthreads();
+    }
+    if (rg == 0 && c < S.mc) {
+        double base_neg = 0.0, prod = 1.0;
+        for (int g = 0; g < S.P.n_gps; ++g)
+            candidate_epilogue(S.P, S.P.gp[g], g, mu_s[g][c], colsq_s[g][c], S.c0 + c, base_neg, prod);
     }
 }
 

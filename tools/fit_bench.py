@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Side measurements for the rows next to the metric path (not the headline bench):
+hyper-parameter fit (device LML + host L-BFGS-B) and a complete suggest() at BASELINE sizes."""
+import json
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bayesianoptimization_b200 as bo  # noqa: E402
+from sklearn.gaussian_process.kernels import Matern  # noqa: E402
+
+warnings.simplefilter("ignore")
+out = {}
+for n, d in [(1024, 8), (4096, 16)]:
+    rs = np.random.RandomState(0)
+    space = bo.TargetSpace(None, {f"x{i:02d}": (0.0, 1.0) for i in range(d)})
+    X = space.random_sample(n, rs)
+    y = np.sin(X.sum(1)) + 0.1 * np.random.RandomState(0).randn(n)
+    space._params, space._target = X, y
+    gp = bo.B200GaussianProcessRegressor(kernel=Matern(nu=2.5), alpha=1e-6, normalize_y=True,
+                                         n_restarts_optimizer=5, random_state=np.random.RandomState(1))
+    L = bo._lib.lib()
+    gp.fit(X[:256], y[:256])  # warm-up (allocations, module load)
+    l0 = L.b200bo_launch_count()
+    t0 = time.perf_counter()
+    gp.fit(X, y)
+    t_fit = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for _ in range(3):
+        gp.log_marginal_likelihood(gp.kernel_.theta, eval_gradient=True)
+    t_lml = (time.perf_counter() - t0) / 3
+    acq = bo.ExpectedImprovement(xi=0.01)
+    t0 = time.perf_counter()
+    x = acq.suggest(gp, space, n_random=10_000, n_smart=10, fit_gp=False, random_state=np.random.RandomState(2))
+    t_sug = time.perf_counter() - t0
+    f = acq._get_acq(gp=gp)
+    xt = space.random_sample(17, np.random.RandomState(3))
+    f(xt)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        f(xt)
+    t_stencil = (time.perf_counter() - t0) / 50
+    t0 = time.perf_counter()
+    for _ in range(50):
+        f(xt[0])
+    t_single = (time.perf_counter() - t0) / 50
+    out[f"n{n}_d{d}"] = dict(fit_5restarts_s=t_fit, length_scale=float(gp.kernel_.length_scale),
+                             lml_grad_eval_s=t_lml, suggest_nofit_s=t_sug,
+                             acq_call_17pts_ms=1e3 * t_stencil, acq_call_1pt_ms=1e3 * t_single,
+                             launches=int(L.b200bo_launch_count() - l0))
+print(json.dumps(out))

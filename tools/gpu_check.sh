@@ -10,12 +10,18 @@ echo "pytest exit $?"; tail -n 40 gpurun_out/pytest_gpu.log
 echo "== smoke"
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -n 5 gpurun_out/smoke.log
 echo "== microbench"
-timeout 120 tools/_bin/microbench > tools/_bin/microbench.json 2>&1; cat tools/_bin/microbench.json
+timeout 120 tools/_bin/microbench > gpurun_out/microbench.json 2>&1; cat gpurun_out/microbench.json
 if [ "$mode" = "quick" ]; then exit 0; fi
 echo "== bench"
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; cat gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err
+echo "== bench (dfma variant)"
+B200BO_PREDICT_IMPL=dfma timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_dfma.json 2> gpurun_out/bench_dfma.err; cat gpurun_out/bench_dfma.json; tail -n 5 gpurun_out/bench_dfma.err
+
+echo "== fit / suggest side bench"
+timeout 900 python tools/fit_bench.py > gpurun_out/fit_bench.json 2> gpurun_out/fit_bench.err; cat gpurun_out/fit_bench.json; tail -n 3 gpurun_out/fit_bench.err
 echo "== bench reference"
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json
+if [ "$mode" = "bench" ]; then exit 0; fi
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1

@@ -53,6 +53,36 @@ __global__ void dmma16816_kernel(double* out, int iters, double a, double b) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// half the warps issue DMMA, the other half DFMA: do the two fp64 paths share execution units?
+__global__ void mixed_kernel(double* out, int iters, double a, double b) {
+    const int warp = threadIdx.x >> 5;
+    double acc = 0;
+    if (warp & 1) {
+        double x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = threadIdx.x * 1e-3 + i;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = fma(x[i], a, b);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc += x[i];
+    } else {
+        double c[8][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = threadIdx.x + i;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += c[i][0] + c[i][1];
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 template <typename F>
 static float time_ms(F f) {
     cudaEvent_t e0, e1;
@@ -95,6 +125,14 @@ int main() {
         ms = time_ms([&] { dmma16816_kernel<<<blocks, threads>>>(out, iters / 4, 1.0000001, 1e-9); });
         tf = 2.0 * 8 * 2048 * (iters / 4) * (double)warps * blocks / (ms * 1e-3) / 1e12;
         printf(", \"dmma16816_tflops_w%d\": %.2f", warps, tf);
+    }
+    {
+        // 16 warps/SM: 8 DMMA warps (8 mma x 256 FMA per iter) + 8 DFMA warps (16 x 32 FMA per iter)
+        int threads = 512, blocks = sms;
+        float ms = time_ms([&] { mixed_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); });
+        double tf_dmma = 2.0 * 8 * 256 * iters * 8.0 * blocks / (ms * 1e-3) / 1e12;
+        double tf_dfma = 2.0 * 16 * 32 * iters * 8.0 * blocks / (ms * 1e-3) / 1e12;
+        printf(", \"mixed_ms\": %.3f, \"mixed_dmma_tflops\": %.2f, \"mixed_dfma_tflops\": %.2f", ms, tf_dmma, tf_dfma);
     }
     printf("}\n");
     return 0;
