@@ -154,6 +154,8 @@ def run_reference(args, rank, world):
     import threadpoolctl
 
     cores = os.cpu_count()
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is entitled to every host thread
+    threadpoolctl.threadpool_limits(limits=cores)
     for _ in range(max(args.warmup, 1) - 1):
         cpu_reference_rate(X, y, 1024)
     t0 = time.perf_counter()
@@ -174,10 +176,30 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall,
     })
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, torchrun's OMP notice) write to fd 1; the contract is ONE
+    JSON line on stdout.  Point fd 1 at stderr for the whole run and keep the real stdout aside."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -308,6 +330,15 @@ def main():
         k_ms = float(np.mean(kernel_ms))
         flops = flops_per_candidate(N_TRAIN, D) * m
         fp64_peak = 64 * 2 * 148 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12  # DFMA/clk/SM nominal
+        peak_src = ("nominal 64 FMA/clk/SM x 148 SM x sm_max_mhz (fp64 has no tcgen05 path; not in "
+                    "MEASURED_PEAKS.json)")
+        try:
+            mb = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_microbench.json")))
+            fp64_peak = max(v for k, v in mb.items() if k.startswith("dmma"))
+            peak_src = ("measured on this pool: best mma.sync f64 (DMMA) rate of tools/microbench.cu, "
+                        "profiles/r01_fp64_microbench.json (nominal 37.2; MEASURED_PEAKS.json has no fp64 entry)")
+        except Exception:
+            pass
         ach_tf = flops / (k_ms * 1e-3) / 1e12
         hbm_bytes = hbm_model_bytes_per_candidate(N_TRAIN, D, 128) * m
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
@@ -323,8 +354,7 @@ def main():
                 "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": ach_tf / fp64_peak, "traffic": None,
                 "kernel": "predict_acq_kernel", "kernel_ms": k_ms,
-                "peak_source": "nominal 64 DFMA/clk/SM x 148 SM x sm_max_mhz (fp64 has no tcgen05 path; "
-                               "not in MEASURED_PEAKS.json)",
+                "peak_source": peak_src,
                 "algorithmic_flops_per_candidate": flops_per_candidate(N_TRAIN, D),
                 "hbm_model": {"achieved": hbm_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                               "frac": hbm_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "tile_T": 128,
@@ -339,7 +369,7 @@ def main():
                 "value": v, "unit": "candidates/s", "cores": os.cpu_count(), "kind": "port",
                 "sample": f"32768 of the same candidates ({secs:.1f} s): sklearn GaussianProcessRegressor."
                           "predict + restated EI closure (oracle/gp_oracle.py), chunks of 2^14"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

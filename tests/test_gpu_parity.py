@@ -295,6 +295,82 @@ def test_c3_full_size_vs_oracle_and_properties(bo, O):
     assert np.array_equal(f(xt), ys)
 
 
+def _synth(n, d, seed=0):
+    rs = np.random.RandomState(seed)
+    X = rs.uniform(size=(n, d))
+    y = np.sin(X.sum(1)) + 0.1 * rs.randn(n)
+    return X, y
+
+
+def test_c2_full_batch_2pow20(bo, O):
+    """BASELINE configs[1]: d=8, N=1024, EI, one 2^20-candidate batch, fp64.  Full batch on the
+    device; a strided 2^14 subsample against the oracle; selection against numpy on the full
+    vector; tile-position independence (a chunk evaluated alone gives the same bits)."""
+    n, d, m = 1024, 8, 1 << 20
+    X, y = _synth(n, d)
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=0.7)).fit(X, y)
+    st = O.fit_fixed(X, y, length_scale=0.7)
+    a = bo.ExpectedImprovement(xi=0.01)
+    a.y_max = float(y.max())
+    f = a._get_acq(gp=gp)
+    xt = np.random.RandomState(1).uniform(size=(m, d))
+    ys = f(xt)
+    sub = slice(0, m, 64)
+    ref = O.acq_closure(st, O.ACQ_EI, xi=0.01, y_max=float(y.max()))(xt[sub])
+    assert_allclose(ys[sub], ref, rtol=RTOL, atol=1e-14)
+    idx, val, top = f.argmin_topk(xt, 10)
+    assert idx == int(np.argmin(ys)) and val == ys[idx]
+    assert list(top) == list(np.argsort(ys, kind="stable")[:10])
+    for s0 in (0, 128 * 77, 128 * 77 + 5):
+        assert np.array_equal(f(xt[s0:s0 + 20_000]), ys[s0:s0 + 20_000])
+
+
+def test_c4_constrained_poi_full_size(bo, O):
+    """BASELINE configs[3]: d=16, N=2048, PoI x p_constraint with a 2-GP ConstraintModel
+    (lb=[-inf,-0.5], ub=[0.6,0.5]); 2^18 candidates on the device, 4096-point subsample vs oracle."""
+    n, d, m = 2048, 16, 1 << 18
+    X, y = _synth(n, d)
+    c = np.column_stack([np.cos(X.sum(1)), np.sin(2 * X.sum(1))])
+    lb, ub = np.array([-np.inf, -0.5]), np.array([0.6, 0.5])
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=0.7)).fit(X, y)
+    cm = bo.ConstraintModel(None, lb, ub)
+    for mdl, l in zip(cm.model, (0.9, 0.5)):
+        mdl.set_params(kernel=Matern(nu=2.5, length_scale=l), optimizer=None)
+    cm.fit(X, c)
+    allowed = cm.allowed(c)
+    y_max = float(y[allowed].max())
+    a = bo.ProbabilityOfImprovement(xi=0.01)
+    a.y_max = y_max
+    f = a._get_acq(gp=gp, constraint=cm)
+    xt = np.random.RandomState(1).uniform(size=(m, d))
+    ys = f(xt)
+    st = O.fit_fixed(X, y, length_scale=0.7)
+    cs = [O.fit_fixed(X, c[:, j], length_scale=l) for j, l in enumerate((0.9, 0.5))]
+    sub = slice(0, m, 64)
+    ref = O.acq_closure(st, O.ACQ_POI, xi=0.01, y_max=y_max, constraint=(cs, lb, ub))(xt[sub])
+    assert_allclose(ys[sub], ref, rtol=RTOL, atol=1e-14)
+    idx, val, top = f.argmin_topk(xt, 10)
+    assert idx == int(np.argmin(ys)) and list(top) == list(np.argsort(ys, kind="stable")[:10])
+
+
+def test_c5_n8192_d32_ucb_shard(bo, O):
+    """BASELINE configs[4]: d=32, N=8192, UCB kappa=2.576 - one GPU's shard (2^19 candidates) of
+    the 8-GPU job; 2048-point subsample vs oracle; shard-local selection vs numpy."""
+    n, d, m = 8192, 32, 1 << 19
+    X, y = _synth(n, d)
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=1.0)).fit(X, y)
+    f = bo.UpperConfidenceBound(kappa=2.576)._get_acq(gp=gp)
+    xt = np.random.RandomState(1).uniform(size=(m, d))
+    ys = f(xt)
+    st = O.fit_fixed(X, y, length_scale=1.0)
+    assert_allclose(gp.L_[-64:], st.L[-64:], rtol=1e-6, atol=1e-10)
+    sub = slice(0, m, 256)
+    ref = O.acq_closure(st, O.ACQ_UCB, kappa=2.576)(xt[sub])
+    assert_allclose(ys[sub], ref, rtol=RTOL, atol=1e-12)
+    idx, val, top = f.argmin_topk(xt, 10)
+    assert idx == int(np.argmin(ys)) and list(top) == list(np.argsort(ys, kind="stable")[:10])
+
+
 @pytest.mark.parametrize("n,d", [(40, 2), (700, 5), (2048, 16)])
 def test_small_batch_path_vs_tiled_and_oracle(bo, O, n, d, monkeypatch):
     """The small-batch kernels (single rows / FD stencils) against the tiled kernel and the oracle,
