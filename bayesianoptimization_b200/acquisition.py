@@ -73,8 +73,14 @@ class FusedAcquisition:
         spec.n_gps = n
         self.spec = spec
 
-    def __call__(self, x):
+    def _candidates(self, x):
         x = B.c_f64(np.asarray(x, dtype=np.float64).reshape(-1, self.dim))
+        if not np.isfinite(x).all():  # sklearn's predict raises the same way (validate_data)
+            raise ValueError("Input X contains NaN or infinity.")
+        return x
+
+    def __call__(self, x):
+        x = self._candidates(x)
         out = np.empty(x.shape[0])
         B.check(B.lib().b200bo_acq_eval(C.byref(self.spec), B.as_dp(x), x.shape[0], B.as_dp(out)))
         return out
@@ -82,7 +88,7 @@ class FusedAcquisition:
     def argmin_topk(self, x, k):
         """Evaluate + np.argmin + k smallest (value, index) on the device
         (R/bayes_opt/acquisition.py:312-317)."""
-        x = B.c_f64(np.asarray(x, dtype=np.float64).reshape(-1, self.dim))
+        x = self._candidates(x)
         best_val = C.c_double()
         best_idx = C.c_int64()
         tv = np.empty(max(k, 1))

@@ -10,22 +10,78 @@ namespace b200bo {
 
 constexpr int kPad = 128;  // training-set size is padded to a multiple of this
 
+// ---- branch-free fp64 primitives for the covariance functions -----------------------------
+// The kernel-matrix builders evaluate sqrt and exp for every (training point, candidate) pair
+// with only a few resident warps, so data-dependent slow-path branches (libm special cases) and
+// their code size hurt more than the arithmetic.  Both routines are <= 1 ulp from libm on their
+// domain (checked against numpy over 3e5 random arguments), far inside the 1e-5 parity bar.
+
+// sqrt(x) for x >= 0 (arguments below 1e-30 are treated as 1e-30: |error| <= 1e-15 absolute).
+__device__ __forceinline__ double sqrt_pos(double x) {
+    const double xc = fmax(x, 1e-30);
+    double y = (double)rsqrtf((float)xc);  // 2^-23 seed
+    const double h = 0.5 * xc;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    double s = xc * y;
+    s = fma(fma(-s, s, xc), 0.5 * y, s);
+    return s;
+}
+
+// exp(-k) for k >= 0 (k > 700 is clamped: the result, < 1e-304, is irrelevant at fp64 scale).
+__device__ __forceinline__ double exp_neg(double k) {
+    k = fmin(k, 700.0);
+    const double n = rint(-k * 1.4426950408889634074);
+    double r = fma(n, -6.93147180369123816490e-01, -k);
+    r = fma(n, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;               // 1/13!
+    p = fma(p, r, 2.0876756987868100e-09);           // 1/12!
+    p = fma(p, r, 2.5052108385441720e-08);           // 1/11!
+    p = fma(p, r, 2.7557319223985893e-07);           // 1/10!
+    p = fma(p, r, 2.7557319223985888e-06);           // 1/9!
+    p = fma(p, r, 2.4801587301587302e-05);           // 1/8!
+    p = fma(p, r, 1.9841269841269841e-04);           // 1/7!
+    p = fma(p, r, 1.3888888888888889e-03);           // 1/6!
+    p = fma(p, r, 8.3333333333333332e-03);           // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);           // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);           // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const long long e = ((long long)n + 1023ll) << 52;  // 2^n, n in [-1010, 0]
+    return p * __longlong_as_double(e);
+}
+
 // ---- covariance functions -------------------------------------------------------------
+// COV codes: 0 = Matern nu=0.5, 1 = nu=1.5, 2 = nu=2.5, 3 = RBF / Matern nu=inf.
 // Follows SK/gaussian_process/kernels.py:1722-1731 (Matern) and :1549/:1553 (RBF) operation by
 // operation: dists = sqrt(r2); nu=2.5: K = dists*sqrt(5); (1 + K + K^2/3) * exp(-K).
-__device__ __forceinline__ double cov_from_r2(double r2, int family, int nu) {
-    if (family == B200BO_KERNEL_RBF) return exp(-0.5 * r2);
-    const double dist = sqrt(r2);
-    if (nu == B200BO_NU_25) {
+template <int COV>
+__device__ __forceinline__ double cov_eval(double r2) {
+    if (COV == 3) return exp_neg(0.5 * r2);
+    const double dist = sqrt_pos(r2);
+    if (COV == 2) {
         const double k = dist * 2.23606797749978969641;  // math.sqrt(5)
-        return (1.0 + k + k * k / 3.0) * exp(-k);
+        return (1.0 + k + k * k / 3.0) * exp_neg(k);
     }
-    if (nu == B200BO_NU_15) {
+    if (COV == 1) {
         const double k = dist * 1.73205080756887729353;  // math.sqrt(3)
-        return (1.0 + k) * exp(-k);
+        return (1.0 + k) * exp_neg(k);
     }
-    if (nu == B200BO_NU_05) return exp(-dist);
-    return exp(-(dist * dist) / 2.0);  // nu = inf
+    return exp_neg(dist);
+}
+
+__host__ __device__ __forceinline__ int cov_code(int family, int nu) {
+    return (family == B200BO_KERNEL_RBF || nu == B200BO_NU_INF) ? 3 : nu;
+}
+
+__device__ __forceinline__ double cov_from_r2(double r2, int family, int nu) {
+    switch (cov_code(family, nu)) {
+        case 0: return cov_eval<0>(r2);
+        case 1: return cov_eval<1>(r2);
+        case 2: return cov_eval<2>(r2);
+        default: return cov_eval<3>(r2);
+    }
 }
 
 // scipy.special.ndtr (cephes ndtr.c), which scipy.stats.norm.cdf evaluates

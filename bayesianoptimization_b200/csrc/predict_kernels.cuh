@@ -55,7 +55,8 @@ constexpr int PBM = 128, PBN = 128, PBK = 16, PSTAGES = 3, PNT = 256;
 // columns of an m8n8k4 fragment); a row stride of 264 words = 8 (mod 32) puts the four k-rows of
 // each half-warp on disjoint bank octets -> 2 wavefronts per request, the minimum for 256 bytes.
 constexpr int PSTR_DFMA = 128, PSTR_DMMA = 132;
-constexpr int kPredictSmemBytesDfma = PSTAGES * PBK * 2 * PSTR_DFMA * 8;  // 98304
+// phase A needs (128 + 2*64) * d doubles (d <= 64 -> 128 KiB); phase B (DFMA) 96 KiB
+constexpr int kPredictSmemBytesDfma = 131072;
 constexpr int PBK_DMMA = 32;  // k-tile of the DMMA variant (one CTA barrier per 32 k)
 constexpr int kPredictSmemBytesDmma = PSTAGES * PBK_DMMA * 2 * PSTR_DMMA * 8;  // 202752
 constexpr int kPredictMaxDimRegs = 16;  // candidates held in registers when d <= 16
@@ -110,14 +111,20 @@ __device__ __forceinline__ void candidate_epilogue(const PredictParams& P, const
 }
 
 // ---- phase A: K*^T tile (np x 128) into the CTA's scratch + K* alpha_ ---------------------------
-// DREG: candidate coordinates in registers (d <= 16, zero padded) - one 16-byte uniform load of the
-// training row serves two dimensions; generic path keeps the candidate tile in shared memory.
-template <bool DREG>
-__device__ __forceinline__ void predict_phase_a(const PredictParams& P, const GpDev& G, long long c0,
-                                                double* __restrict__ Ks, double* xc_s,
-                                                double (*mu_s)[PBN]) {
+// Thread = one candidate column (two threads per column split the rows).  Training rows stream
+// through shared memory in chunks of 64 (double-buffered cp.async), so every row read is a
+// warp-wide broadcast LDS; DREG keeps the candidate's coordinates in registers (d <= 16).
+// COV is a template parameter so that the covariance is branch-free straight-line code.
+constexpr int PA_CHUNK = 64;  // training rows per staged chunk
+
+template <bool DREG, int COV>
+__device__ __forceinline__ void predict_phase_a_impl(const PredictParams& P, const GpDev& G, long long c0,
+                                                     double* __restrict__ Ks, double* smem,
+                                                     double (*mu_s)[PBN]) {
     const int tid = threadIdx.x;
     const int d = P.d, np = G.np;
+    double* xc_s = smem;                       // [d][PBN]
+    double* xs_s = smem + (size_t)d * PBN;     // [2][PA_CHUNK][d]
     for (int idx = tid; idx < PBN * d; idx += PNT) {
         const int c = idx / d, j = idx - c * d;
         const long long gi = c0 + c;
@@ -129,79 +136,95 @@ __device__ __forceinline__ void predict_phase_a(const PredictParams& P, const Gp
         }
         xc_s[j * PBN + c] = v;
     }
-    __syncthreads();
+    const int chunk_pieces = PA_CHUNK * d / 2;  // 16-byte pieces per chunk (PA_CHUNK*d is even)
+    auto load_chunk = [&](int buf, int ch) {
+        const double* src = G.Xs + (size_t)ch * PA_CHUNK * d;
+        double* dst = xs_s + (size_t)buf * PA_CHUNK * d;
+        for (int q = tid; q < chunk_pieces; q += PNT) cp_async16_cg(dst + 2 * q, src + 2 * q);
+    };
+    const int nch = np / PA_CHUNK;
+    load_chunk(0, 0);
+    cp_async_commit();
+    __syncthreads();  // xc_s visible
     const int c = tid & (PBN - 1), half = tid >> 7;
-    double mu_acc = 0.0;
+    double xc[kPredictMaxDimRegs];
     if (DREG) {
-        double xc[kPredictMaxDimRegs];
 #pragma unroll
         for (int j = 0; j < kPredictMaxDimRegs; ++j) xc[j] = (j < d) ? xc_s[j * PBN + c] : 0.0;
-        const int dp = (d + 1) & ~1;  // Xs rows are read two dimensions at a time
-        constexpr int R = 8;  // rows per iteration: 8 independent distance chains per thread
-        for (int n0 = half * R; n0 < np; n0 += 2 * R) {
+    }
+    double mu_acc = 0.0;
+    constexpr int R = 8;
+    for (int ch = 0; ch < nch; ++ch) {
+        if (ch + 1 < nch) load_chunk((ch + 1) & 1, ch + 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const double* xs = xs_s + (size_t)(ch & 1) * PA_CHUNK * d;
+        for (int r0 = half * (PA_CHUNK / 2); r0 < (half + 1) * (PA_CHUNK / 2); r0 += R) {
             double r2[R];
 #pragma unroll
             for (int q = 0; q < R; ++q) r2[q] = 0.0;
-            const double* x0 = G.Xs + (size_t)n0 * d;
-            if ((d & 1) == 0) {
+            if (DREG && (d & 1) == 0) {
 #pragma unroll
                 for (int j = 0; j < kPredictMaxDimRegs; j += 2) {
-                    if (j < dp) {
+                    if (j < d) {
 #pragma unroll
                         for (int q = 0; q < R; ++q) {
-                            const double2 xv = __ldg(reinterpret_cast<const double2*>(x0 + q * d + j));
+                            const double2 xv = *reinterpret_cast<const double2*>(xs + (r0 + q) * d + j);
                             const double d0 = xc[j] - xv.x, d1 = xc[j + 1] - xv.y;
                             r2[q] = fma(d0, d0, r2[q]);
                             r2[q] = fma(d1, d1, r2[q]);
                         }
                     }
                 }
-            } else {
+            } else if (DREG) {
 #pragma unroll
                 for (int j = 0; j < kPredictMaxDimRegs; ++j) {
                     if (j < d) {
 #pragma unroll
                         for (int q = 0; q < R; ++q) {
-                            const double df = xc[j] - __ldg(x0 + q * d + j);
+                            const double df = xc[j] - xs[(r0 + q) * d + j];
                             r2[q] = fma(df, df, r2[q]);
                         }
+                    }
+                }
+            } else {
+                for (int j = 0; j < d; ++j) {
+                    const double xv = xc_s[j * PBN + c];
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {
+                        const double df = xv - xs[(r0 + q) * d + j];
+                        r2[q] = fma(df, df, r2[q]);
                     }
                 }
             }
 #pragma unroll
             for (int q = 0; q < R; ++q) {
-                const int n = n0 + q;
-                double kv = 0.0;
-                if (n < G.n) kv = G.constv * cov_from_r2(r2[q], G.family, G.nu);
+                const int n = ch * PA_CHUNK + r0 + q;
+                double kv = G.constv * cov_eval<COV>(r2[q]);
+                if (n >= G.n) kv = 0.0;
                 Ks[(size_t)n * PBN + c] = kv;
                 mu_acc = fma(__ldg(G.alphav + n), kv, mu_acc);
             }
         }
-    } else {
-        for (int n0 = half * 4; n0 < np; n0 += 8) {
-            double r2[4] = {0.0, 0.0, 0.0, 0.0};
-            const double* x0 = G.Xs + (size_t)n0 * d;
-            for (int j = 0; j < d; ++j) {
-                const double xv = xc_s[j * PBN + c];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const double df = xv - __ldg(x0 + q * d + j);
-                    r2[q] = fma(df, df, r2[q]);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int n = n0 + q;
-                double kv = 0.0;
-                if (n < G.n) kv = G.constv * cov_from_r2(r2[q], G.family, G.nu);
-                Ks[(size_t)n * PBN + c] = kv;
-                mu_acc = fma(__ldg(G.alphav + n), kv, mu_acc);
-            }
-        }
+        __syncthreads();  // chunk buffer free for the prefetch of chunk ch+2
     }
+    cp_async_wait<0>();
     mu_s[half][c] = mu_acc;
     __threadfence_block();
     __syncthreads();
+}
+
+template <bool DREG>
+__device__ __forceinline__ void predict_phase_a(const PredictParams& P, const GpDev& G, long long c0,
+                                                double* __restrict__ Ks, double* smem,
+                                                double (*mu_s)[PBN]) {
+    switch (cov_code(G.family, G.nu)) {
+        case 0: predict_phase_a_impl<DREG, 0>(P, G, c0, Ks, smem, mu_s); break;
+        case 1: predict_phase_a_impl<DREG, 1>(P, G, c0, Ks, smem, mu_s); break;
+        case 2: predict_phase_a_impl<DREG, 2>(P, G, c0, Ks, smem, mu_s); break;
+        default: predict_phase_a_impl<DREG, 3>(P, G, c0, Ks, smem, mu_s); break;
+    }
 }
 
 // stage loader shared by both GEMM variants: BK k-rows x 128 doubles of LinvT and of K*
@@ -300,7 +323,11 @@ __device__ __forceinline__ void predict_phase_b_dmma(const GpDev& G, const doubl
                                                      double* smem) {
     constexpr int STR = PSTR_DMMA, BK = PBK_DMMA;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp & 3, wn = warp >> 2;
+    // warps w and w+4 share an SM sub-partition: give them row slabs s and 3-s so that skipping
+    // the structurally-zero part of the diagonal block (k beyond the slab's last row) leaves every
+    // sub-partition with the same amount of work
+    const int wn = warp >> 2;
+    const int wm = wn ? 3 - (warp & 3) : (warp & 3);
     const int g = lane >> 2, t4 = lane & 3;
     const int np = G.np;
     double* As = smem;
@@ -332,6 +359,9 @@ __device__ __forceinline__ void predict_phase_b_dmma(const GpDev& G, const doubl
                 predict_load_stage<STR, BK>(As + (nxt % PSTAGES) * BK * STR, Bs + (nxt % PSTAGES) * BK * STR,
                                             Abase + (size_t)(nxt * BK) * np, Ks + (size_t)(nxt * BK) * PBN, np);
             cp_async_commit();
+            // diagonal block of L^-1 (k in [ib*128, ib*128+128)): rows wm*32.. have zeros for
+            // k > row, so the k-tiles beyond this warp's slab contribute nothing
+            if (ks * BK >= ib * PBM + (wm + 1) * 32) continue;
             const double* as = As + (ks % PSTAGES) * BK * STR + wm * 32 + g;
             const double* bs = Bs + (ks % PSTAGES) * BK * STR + wn * 64 + g;
 #pragma unroll
