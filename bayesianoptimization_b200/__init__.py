@@ -12,6 +12,7 @@ from .acquisition import (
     ConstantLiar,
     ExpectedImprovement,
     FusedAcquisition,
+    GPHedge,
     ProbabilityOfImprovement,
     UpperConfidenceBound,
 )
@@ -23,7 +24,7 @@ from .space import TargetSpace
 __version__ = "0.1.0"
 
 __all__ = [
-    "AcquisitionFunction", "ConstantLiar", "ExpectedImprovement", "FusedAcquisition",
+    "AcquisitionFunction", "ConstantLiar", "ExpectedImprovement", "FusedAcquisition", "GPHedge",
     "ProbabilityOfImprovement", "UpperConfidenceBound", "ConstraintModel",
     "B200GaussianProcessRegressor", "TargetSpace", "enable", "accelerate_acquisition",
     "to_b200_gp", "build_library", "__version__",

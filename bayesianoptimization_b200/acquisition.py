@@ -20,7 +20,11 @@ from copy import deepcopy
 
 import numpy as np
 from numpy.random import RandomState
+from packaging import version
+from scipy import __version__ as scipy_version
 from scipy.optimize import minimize
+from scipy.optimize._differentialevolution import DifferentialEvolutionSolver
+from scipy.special import softmax
 from scipy.stats import norm
 
 from . import _lib as B
@@ -224,9 +228,37 @@ class AcquisitionFunction(abc.ABC):
                     x_min = x_try
                     min_acq = np.squeeze(res.fun)
         else:
-            raise NotImplementedError(
-                "mixed-integer acquisition optimisation (DifferentialEvolutionSolver branch, "
-                "R/bayes_opt/acquisition.py:376-412) is not on the accelerated path yet")
+            # mixed-integer branch (R/bayes_opt/acquisition.py:376-412): SciPy's differential
+            # evolution over all dimensions seeded with x_seeds, then an L-BFGS-B polish of the
+            # continuous ones.  Host driver as in the reference; every objective call is a device
+            # call (small-batch kernels); DE's immediate-updating semantics are kept.
+            xinit = space.random_sample(15 * len(space.bounds), random_state=random_state)
+            if len(x_seeds) > 0:
+                n_seeds = min(len(x_seeds), len(xinit))
+                xinit[:n_seeds] = x_seeds[:n_seeds]
+            de_parameters = {"func": acq, "bounds": space.bounds, "polish": False, "init": xinit}
+            if version.parse(scipy_version) < version.parse("1.15.0"):
+                de_parameters["seed"] = random_state
+            else:
+                de_parameters["rng"] = random_state
+            de = DifferentialEvolutionSolver(**de_parameters)
+            res_de = de.solve()
+            if not res_de.success:
+                raise RuntimeError(f"Differential evolution optimization failed. Message: {res_de.message}")
+            x_min = res_de.x
+            min_acq = np.squeeze(res_de.fun)
+            if any(continuous_dimensions):
+                x_try = x_min.copy()
+
+                def continuous_acq(x, x_try=x_try):
+                    x_try[continuous_dimensions] = x
+                    return acq(x_try)
+
+                res = minimize(continuous_acq, x_min[continuous_dimensions], bounds=continuous_bounds)
+                if res.success and np.squeeze(res.fun) < min_acq:
+                    x_try[continuous_dimensions] = res.x
+                    x_min = x_try
+                    min_acq = np.squeeze(res.fun)
         if min_acq is None:
             min_acq = np.inf
             x_min = np.array([np.nan] * space.bounds.shape[0])
@@ -466,3 +498,76 @@ class ConstantLiar(AcquisitionFunction):
         self.strategy = params["strategy"]
         self.atol = params["atol"]
         self.rtol = params["rtol"]
+
+
+class GPHedge(AcquisitionFunction):
+    """Portfolio of base acquisitions chosen by softmax of cumulative rewards
+    (R/bayes_opt/acquisition.py:1181-1360).  Host logic; the rewards (posterior means of the previous
+    candidates) and every base ``suggest`` run on the device."""
+
+    def __init__(self, base_acquisitions, random_state=None):
+        super().__init__(random_state)
+        self.base_acquisitions = list(base_acquisitions)
+        self.n_acq = len(self.base_acquisitions)
+        self.gains = np.zeros(self.n_acq)
+        self.previous_candidates = None
+
+    def base_acq(self, *args, **kwargs):
+        msg = ("GPHedge base acquisition function is ambiguous."
+               " You may use self.base_acquisitions[i].base_acq(mean, std)"
+               " to get the base acquisition function for the i-th acquisition.")
+        raise TypeError(msg)
+
+    def _sample_idx_from_softmax_gains(self, random_state):
+        cumsum_softmax_g = np.cumsum(softmax(self.gains))
+        r = random_state.rand()
+        return np.argmax(r <= cumsum_softmax_g)
+
+    def _update_gains(self, gp):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            rewards = gp.predict(self.previous_candidates)
+        self.gains += rewards
+        self.previous_candidates = None
+
+    def suggest(self, gp, target_space, n_random=10_000, n_smart=10, fit_gp=True, random_state=None):
+        if len(target_space) == 0:
+            msg = ("Cannot suggest a point without previous samples. Use "
+                   " target_space.random_sample() to generate a point and "
+                   " target_space.probe(*) to evaluate it.")
+            raise TargetSpaceEmptyError(msg)
+        self.i += 1
+        random_state = ensure_rng(random_state)
+        if fit_gp:
+            self._fit_gp(gp=gp, target_space=target_space)
+        if self.previous_candidates is not None:
+            self._update_gains(gp)
+        x_max = [
+            base_acq.suggest(gp=gp, target_space=target_space, n_random=n_random // self.n_acq,
+                             n_smart=n_smart // self.n_acq, fit_gp=False, random_state=random_state)
+            for base_acq in self.base_acquisitions
+        ]
+        self.previous_candidates = np.array(x_max)
+        idx = self._sample_idx_from_softmax_gains(random_state=random_state)
+        if not target_space._allow_duplicate_points and x_max[idx] in target_space:
+            non_duplicate_idx = [i for i, x in enumerate(x_max) if x not in target_space]
+            if len(non_duplicate_idx) > 0:
+                cumsum_softmax_g = np.cumsum(softmax(self.gains[non_duplicate_idx]))
+                r = random_state.rand()
+                idx = non_duplicate_idx[np.argmax(r <= cumsum_softmax_g)]
+        return x_max[idx]
+
+    def get_acquisition_params(self):
+        return {
+            "base_acquisitions_params": [acq.get_acquisition_params() for acq in self.base_acquisitions],
+            "gains": self.gains.tolist(),
+            "previous_candidates": self.previous_candidates.tolist()
+            if self.previous_candidates is not None else None,
+        }
+
+    def set_acquisition_params(self, params):
+        for acq, acq_params in zip(self.base_acquisitions, params["base_acquisitions_params"]):
+            acq.set_acquisition_params(acq_params)
+        self.gains = np.array(params["gains"])
+        self.previous_candidates = (
+            np.array(params["previous_candidates"]) if params["previous_candidates"] is not None else None)

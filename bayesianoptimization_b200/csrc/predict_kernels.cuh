@@ -355,27 +355,33 @@ __device__ __forceinline__ void predict_phase_b_dmma(const GpDev& G, const doubl
             cp_async_wait<PSTAGES - 2>();
             __syncthreads();
             const int nxt = ks + PSTAGES - 1;
-            if (nxt < nks)
-                predict_load_stage<STR, BK>(As + (nxt % PSTAGES) * BK * STR, Bs + (nxt % PSTAGES) * BK * STR,
-                                            Abase + (size_t)(nxt * BK) * np, Ks + (size_t)(nxt * BK) * PBN, np);
-            cp_async_commit();
             // diagonal block of L^-1 (k in [ib*128, ib*128+128)): rows wm*32.. have zeros for
             // k > row, so the k-tiles beyond this warp's slab contribute nothing
-            if (ks * BK >= ib * PBM + (wm + 1) * 32) continue;
+            const bool live = ks * BK < ib * PBM + (wm + 1) * 32;
             const double* as = As + (ks % PSTAGES) * BK * STR + wm * 32 + g;
             const double* bs = Bs + (ks % PSTAGES) * BK * STR + wn * 64 + g;
 #pragma unroll
             for (int k4 = 0; k4 < BK / 4; ++k4) {
-                double a[4], b[8];
-                const int krow = (k4 * 4 + t4) * STR;
+                if (k4 == 1) {
+                    // prefetch issued behind the first batch of MMAs so the tensor pipe is already
+                    // busy while the LDGSTS addresses are generated
+                    if (nxt < nks)
+                        predict_load_stage<STR, BK>(As + (nxt % PSTAGES) * BK * STR, Bs + (nxt % PSTAGES) * BK * STR,
+                                                    Abase + (size_t)(nxt * BK) * np, Ks + (size_t)(nxt * BK) * PBN, np);
+                    cp_async_commit();
+                }
+                if (live) {
+                    double a[4], b[8];
+                    const int krow = (k4 * 4 + t4) * STR;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = as[krow + i * 8];
+                    for (int i = 0; i < 4; ++i) a[i] = as[krow + i * 8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) b[j] = bs[krow + j * 8];
+                    for (int j = 0; j < 8; ++j) b[j] = bs[krow + j * 8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                        for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                }
             }
         }
         cp_async_wait<0>();

@@ -39,6 +39,9 @@ def accelerate_acquisition(acq):
         acq.base_acquisition = accelerate_acquisition(acq.base_acquisition)
         hooks = A.AcquisitionFunction
         kind = None
+    elif name == "GPHedge":
+        acq.base_acquisitions = [accelerate_acquisition(a) for a in acq.base_acquisitions]
+        return acq  # GPHedge itself only orchestrates; its bases and gp.predict run on the device
     elif name in _DEVICE_KINDS:
         hooks = _DEVICE_KINDS[name]
         kind = hooks._b200_kind

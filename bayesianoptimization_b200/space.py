@@ -1,5 +1,5 @@
 """Minimal host-side mirror of bayes_opt.target_space.TargetSpace (R/bayes_opt/target_space.py)
-for float parameters: just what the acquisition hot path reads.
+for float and int parameters: just what the acquisition hot path reads.
 
 It exists so that the parity tests, bench.py and smoke() can drive the acquisition classes on
 the GPU box, where the reference package is not installed.  With the reference installed, pass
@@ -30,7 +30,14 @@ class TargetSpace:
                  allow_duplicate_points=False):
         self.target_func = target_func
         self._keys = list(pbounds.keys())  # R/bayes_opt/target_space.py:88 (insertion order)
-        self._bounds = np.array([pbounds[k] for k in self._keys], dtype=float)
+        # (lo, hi) or (lo, hi, float) -> float parameter; (lo, hi, int) -> int parameter
+        # (R/bayes_opt/target_space.py:252-262); categorical parameters are not mirrored
+        self._is_int = np.array([len(pbounds[k]) == 3 and pbounds[k][2] is int for k in self._keys])
+        for k in self._keys:
+            b = pbounds[k]
+            if not (len(b) == 2 or (len(b) == 3 and b[2] in (int, float))):
+                raise NotImplementedError("only float and int parameters are mirrored here")
+        self._bounds = np.array([pbounds[k][:2] for k in self._keys], dtype=float)
         self._dim = len(self._keys)
         self._params = np.empty((0, self._dim))
         self._target = np.empty((0,))
@@ -46,6 +53,9 @@ class TargetSpace:
 
     def __len__(self):
         return len(self._target)
+
+    def __contains__(self, x):
+        return tuple(float(v) for v in np.asarray(x, dtype=float).ravel()) in self._cache
 
     @property
     def empty(self):
@@ -83,13 +93,18 @@ class TargetSpace:
 
     @property
     def continuous_dimensions(self):
-        return np.ones(self._dim, dtype=bool)
+        return ~self._is_int
 
     def kernel_transform(self, value):
-        return np.atleast_2d(value)
+        """Identity for floats, np.round for ints (R/bayes_opt/parameter.py:222-234, :308-320)."""
+        value = np.array(np.atleast_2d(value), dtype=float)
+        if self._is_int.any():
+            value[:, self._is_int] = np.round(value[:, self._is_int])
+        return value
 
     def array_to_params(self, x):
-        return dict(zip(self._keys, np.asarray(x, dtype=float)))
+        x = np.asarray(x, dtype=float)
+        return {k: (int(np.round(v)) if i else float(v)) for k, v, i in zip(self._keys, x, self._is_int)}
 
     def params_to_array(self, params):
         return np.asarray([params[k] for k in self._keys], dtype=float)
@@ -154,7 +169,11 @@ class TargetSpace:
         n_samples = max(1, n_samples)
         data = np.empty((n_samples, self._dim))
         for j in range(self._dim):
-            data[:, j] = random_state.uniform(self._bounds[j, 0], self._bounds[j, 1], n_samples)
+            if self._is_int[j]:  # IntParameter.random_sample, R/bayes_opt/parameter.py:260-278
+                data[:, j] = random_state.randint(int(self._bounds[j, 0]), int(self._bounds[j, 1]) + 1,
+                                                  n_samples).astype(float)
+            else:
+                data[:, j] = random_state.uniform(self._bounds[j, 0], self._bounds[j, 1], n_samples)
         if flatten:
             return data.ravel()
         return data

@@ -225,6 +225,33 @@ def case_constant_liar():
          suggestions=np.array(sug))
 
 
+def case_mixed_int():
+    """Float + int parameters: np.round kernel transform (R/bayes_opt/parameter.py:308-320) and the
+    DifferentialEvolution branch of _smart_minimize (R/bayes_opt/acquisition.py:376-412)."""
+    def f(x, k):
+        return -((x - 2.2) ** 2) - 0.3 * (k - 4) ** 2
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        space = TargetSpace(f, {"x": (0.0, 5.0), "k": (0, 6, int)})
+        rs = RandomState(2)
+        for _ in range(12):
+            space.probe(space.random_sample(random_state=rs))
+        gp = GaussianProcessRegressor(
+            kernel=wrap_kernel(Matern(nu=2.5, length_scale=1.3), space.kernel_transform), alpha=1e-6,
+            normalize_y=True, optimizer=None)
+        gp.fit(space.params, space.target)
+        ei = acquisition.ExpectedImprovement(xi=0.01)
+        ei.y_max = space.target.max()
+        xt = np.column_stack([RandomState(5).uniform(0, 5, 600), RandomState(6).uniform(-0.49, 6.49, 600)])
+        ys = ei._get_acq(gp=gp)(xt)
+        mu, sd = gp.predict(xt, return_std=True)
+        rng = RandomState(11)
+        sug = ei.suggest(gp, space, n_random=2000, n_smart=4, fit_gp=False, random_state=rng)
+    save("mixed_int_small", X=space.params, y=space.target, xt=xt, acq_ei=ys, mu=mu, sd=sd,
+         y_max=np.float64(space.target.max()), suggestion=sug, rand_draw=space.random_sample(50, RandomState(9)))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     case_readme()
@@ -233,3 +260,4 @@ if __name__ == "__main__":
     case_constrained()
     case_fit_full()
     case_constant_liar()
+    case_mixed_int()

@@ -80,7 +80,7 @@ def test_mirror_classes_match_reference_signatures(ref):
 
     import bayesianoptimization_b200 as bo
 
-    for name in ("UpperConfidenceBound", "ProbabilityOfImprovement", "ExpectedImprovement", "ConstantLiar"):
+    for name in ("UpperConfidenceBound", "ProbabilityOfImprovement", "ExpectedImprovement", "ConstantLiar", "GPHedge"):
         r, m = getattr(ref.acquisition, name), getattr(bo, name)
         assert list(inspect.signature(r.__init__).parameters) == list(inspect.signature(m.__init__).parameters), name
         assert list(inspect.signature(r.suggest).parameters) == list(inspect.signature(m.suggest).parameters), name

@@ -666,3 +666,51 @@ def test_constrained_suggest_runs_and_respects_errors(bo):
     assert x.shape == (2,) and np.all(x >= space.bounds[:, 0]) and np.all(x <= space.bounds[:, 1])
     with pytest.raises(ConstraintNotSupportedError):
         bo.UpperConfidenceBound().suggest(gp, space, random_state=rs)
+
+
+def test_gphedge_runs_and_updates_gains(bo):
+    """GPHedge (R/bayes_opt/acquisition.py:1181-1360) over device base acquisitions."""
+    space = bo.TargetSpace(lambda x, y: -((x - 3) ** 2) - (y - 1) ** 2, {"x": (1, 4), "y": (0, 3.0)})
+    rs = np.random.RandomState(0)
+    for _ in range(6):
+        space.probe(space.random_sample(random_state=rs))
+    gp = bo.B200GaussianProcessRegressor(kernel=Matern(nu=2.5), alpha=1e-6, normalize_y=True,
+                                         n_restarts_optimizer=2, random_state=np.random.RandomState(0))
+    hedge = bo.GPHedge([bo.UpperConfidenceBound(kappa=2.0), bo.ExpectedImprovement(xi=0.01),
+                        bo.ProbabilityOfImprovement(xi=0.01)])
+    x1 = hedge.suggest(gp, space, n_random=3000, n_smart=3, random_state=rs)
+    assert x1.shape == (2,) and hedge.previous_candidates.shape == (3, 2)
+    space.probe(x1)
+    x2 = hedge.suggest(gp, space, n_random=3000, n_smart=3, random_state=rs)
+    assert np.any(hedge.gains != 0) and x2.shape == (2,)
+    p = hedge.get_acquisition_params()
+    h2 = bo.GPHedge([bo.UpperConfidenceBound(kappa=2.0), bo.ExpectedImprovement(xi=0.01),
+                     bo.ProbabilityOfImprovement(xi=0.01)])
+    h2.set_acquisition_params(p)
+    assert h2.get_acquisition_params() == p
+    with pytest.raises(TypeError):
+        hedge.base_acq(0, 1)
+
+
+def test_mixed_int_space_round_transform_and_de_branch(bo, golden):
+    """Float + int parameters: device np.round transform vs the reference's values, then the
+    DifferentialEvolution + polish branch of _smart_minimize from the same RNG state."""
+    from bayesianoptimization_b200.kernels import wrap_kernel
+
+    g = golden("mixed_int_small")
+    space = bo.TargetSpace(None, {"x": (0.0, 5.0), "k": (0, 6, int)})
+    assert np.array_equal(space.random_sample(50, np.random.RandomState(9)), g["rand_draw"])
+    for x, t in zip(g["X"], g["y"]):
+        space.register(x, t)
+    gp = make_gp(bo, wrap_kernel(Matern(nu=2.5, length_scale=1.3), space.kernel_transform)).fit(
+        space.params, space.target)
+    mu, sd = gp.predict(g["xt"], return_std=True)
+    assert_allclose(mu, g["mu"], rtol=RTOL, atol=1e-10)
+    assert_allclose(sd, g["sd"], rtol=RTOL, atol=1e-9)
+    ei = bo.ExpectedImprovement(xi=0.01)
+    ei.y_max = float(g["y_max"])
+    assert_allclose(ei._get_acq(gp=gp)(g["xt"]), g["acq_ei"], rtol=RTOL, atol=1e-14)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sug = ei.suggest(gp, space, n_random=2000, n_smart=4, fit_gp=False, random_state=np.random.RandomState(11))
+    assert_allclose(sug, g["suggestion"], rtol=1e-5, atol=1e-5)

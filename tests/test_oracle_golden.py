@@ -126,3 +126,19 @@ def test_oracle_vs_live_sklearn(kern, kw):
     v, g = O.lml_and_grad(X, st.y_norm, **kw)
     assert v == pytest.approx(v0, rel=1e-10)
     assert_allclose(g, g0, rtol=1e-7, atol=1e-8)
+
+
+def test_mixed_int_round_transform(golden):
+    g = golden("mixed_int_small")
+
+    def tr(v):
+        v = np.array(np.atleast_2d(v), dtype=float)
+        v[:, 1] = np.round(v[:, 1])
+        return v
+
+    st = O.fit_fixed(tr(g["X"]), g["y"], length_scale=1.3)
+    mu, sd = O.predict(st, tr(g["xt"]))
+    assert_allclose(mu, g["mu"], rtol=1e-9, atol=1e-11)
+    assert_allclose(sd, g["sd"], rtol=1e-8, atol=1e-11)
+    ys = O.acq_closure(st, O.ACQ_EI, xi=0.01, y_max=float(g["y_max"]))(tr(g["xt"]))
+    assert_allclose(ys, g["acq_ei"], rtol=1e-7, atol=1e-14)
