@@ -84,6 +84,10 @@ struct b200bo_gp {
     // small-batch path scratch (per GP) + work-unit tables (rebuilt when np changes)
     DevBuf s_ksm, s_partial, s_mupart, s_unit, s_rb;
     int s_np = 0, s_nunits = 0;
+    // fp32 mode: L^-1 as tf32 (hi,lo) UMMA operand images (built on first use after a fit)
+    DevBuf tc_linv;
+    bool tc_valid = false;
+    int precision = B200BO_PRECISION_FP64;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
@@ -133,6 +137,10 @@ extern "C" int b200bo_gp_create(b200bo_gp** out, int device) {
                             cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDmma));
     CU(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             kPotrfSmemBytes));
+    CU(cudaFuncSetAttribute(predict_acq_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            kPredictSmemBytesTc));
+    CU(cudaFuncSetAttribute(predict_acq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            kPredictSmemBytesTc));
     *out = gp;
     return B200BO_OK;
 }
@@ -143,7 +151,8 @@ extern "C" void b200bo_gp_destroy(b200bo_gp* gp) {
     DevBuf* bufs[] = {&gp->X, &gp->Xs, &gp->y, &gp->K, &gp->L, &gp->W, &gp->WT, &gp->T,
                       &gp->alphav, &gp->v1, &gp->v2, &gp->ls, &gp->xf, &gp->info, &gp->part,
                       &gp->pscratch, &gp->xc, &gp->out_acq, &gp->out_mu, &gp->out_sd, &gp->sel,
-                      &gp->clamp, &gp->s_ksm, &gp->s_partial, &gp->s_mupart, &gp->s_unit, &gp->s_rb};
+                      &gp->clamp, &gp->s_ksm, &gp->s_partial, &gp->s_mupart, &gp->s_unit, &gp->s_rb,
+                      &gp->tc_linv};
     for (DevBuf* b : bufs) b->release();
     if (gp->ev0) cudaEventDestroy(gp->ev0);
     if (gp->ev1) cudaEventDestroy(gp->ev1);
@@ -153,6 +162,14 @@ extern "C" void b200bo_gp_destroy(b200bo_gp* gp) {
 
 extern "C" int64_t b200bo_gp_n(const b200bo_gp* gp) { return gp ? gp->n : 0; }
 extern "C" int b200bo_gp_dim(const b200bo_gp* gp) { return gp ? gp->d : 0; }
+
+extern "C" int b200bo_gp_set_precision(b200bo_gp* gp, int precision) {
+    if (!gp) return set_err(B200BO_ERR_ARG, "gp is NULL");
+    if (precision != B200BO_PRECISION_FP64 && precision != B200BO_PRECISION_FP32)
+        return set_err(B200BO_ERR_ARG, "unknown precision %d", precision);
+    gp->precision = precision;
+    return B200BO_OK;
+}
 
 extern "C" int b200bo_gp_set_transform(b200bo_gp* gp, const int32_t* xform, int d) {
     if (!gp) return set_err(B200BO_ERR_ARG, "gp is NULL");
@@ -182,6 +199,7 @@ extern "C" int b200bo_gp_set_data(b200bo_gp* gp, const double* X, const double* 
         return set_err(B200BO_ERR_ARG, "transform has %zu entries, d=%d", gp->xform.size(), d);
     CU(cudaSetDevice(gp->device));
     gp->fitted = false;
+    gp->tc_valid = false;
     gp->n = n;
     gp->d = d;
     gp->np = round_up(n, kPad);
@@ -408,6 +426,7 @@ extern "C" int b200bo_gp_lml(b200bo_gp* gp, const b200bo_kernel* kern, double al
     if ((rc = check_kernel(gp, kern))) return rc;
     CU(cudaSetDevice(gp->device));
     gp->fitted = false;  // buffers are being overwritten
+    gp->tc_valid = false;
     const int n = (int)gp->n, np = gp->np, d = gp->d;
     const int aniso = kern->n_length_scale > 1;
     const int ntheta = (has_const ? 1 : 0) + kern->n_length_scale;
@@ -529,10 +548,26 @@ static bool use_small_path(long long m, int np_max, int n_gps, int sm_count) {
 // GEMM inner-loop variant of the fused predict kernel: "dmma" (mma.sync m8n8k4 f64, default) or
 // "dfma" (8x8 register tiles).  Both are exact fp64 with fixed-order reductions; the environment
 // variable B200BO_PREDICT_IMPL selects one for A/B measurements.
-static int predict_impl() {
+static int predict_impl(int precision) {
     const char* e = getenv("B200BO_PREDICT_IMPL");
     if (e && (e[0] == 'd' || e[0] == 'D') && (e[1] == 'f' || e[1] == 'F')) return PREDICT_IMPL_DFMA;
-    return PREDICT_IMPL_DMMA;
+    if (e && (e[0] == 't' || e[0] == 'T')) return PREDICT_IMPL_TF32;  // "tf32": fp32 mode on tcgen05
+    if (e && (e[0] == 'd' || e[0] == 'D')) return PREDICT_IMPL_DMMA;
+    return precision == B200BO_PRECISION_FP32 ? PREDICT_IMPL_TF32 : PREDICT_IMPL_DMMA;
+}
+
+// fp32 mode operand images of L^-1 (once per fit)
+static int ensure_tc(b200bo_gp* gp, cudaStream_t stream) {
+    if (gp->tc_valid) return B200BO_OK;
+    const int np = gp->np;
+    int rc;
+    if ((rc = gp->tc_linv.reserve((size_t)(np / PBM) * (np / tc::kTcK) * 2 * tc::kTcImgBytes))) return rc;
+    dim3 grid(np / tc::kTcK, np / PBM);
+    pretile_linv_tc_kernel<<<grid, 256, 0, stream>>>(gp->W.as<double>(), np, gp->tc_linv.as<uint8_t>());
+    LAUNCHED();
+    CU(cudaGetLastError());
+    gp->tc_valid = true;
+    return B200BO_OK;
 }
 
 static int check_spec(const b200bo_acq* spec) {
@@ -581,6 +616,7 @@ extern "C" int b200bo_acq_eval_dev(const b200bo_acq* spec, const double* d_Xc, i
         G.alphav = gp->alphav.as<double>();
         G.ls = gp->ls.as<double>();
         G.xform = gp->xform.empty() ? nullptr : gp->xf.as<int>();
+        G.linv_tc = nullptr;
         G.n = (int)gp->n;
         G.np = gp->np;
         G.family = gp->family;
@@ -644,7 +680,17 @@ extern "C" int b200bo_acq_eval_dev(const b200bo_acq* spec, const double* d_Xc, i
         P.scratch = g0->pscratch.as<double>();
         CU(cudaEventRecord(g0->ev0, stream));
         const bool dreg = P.d <= kPredictMaxDimRegs;
-        if (predict_impl() == PREDICT_IMPL_DMMA) {
+        if (predict_impl(g0->precision) == PREDICT_IMPL_TF32) {
+            for (int g = 0; g < spec->n_gps; ++g) {
+                if ((rc = ensure_tc(spec->gps[g], stream))) return rc;
+                P.gp[g].linv_tc = spec->gps[g]->tc_linv.as<uint8_t>();
+            }
+            CU(cudaEventRecord(g0->ev0, stream));  // exclude the one-off tiling from the kernel time
+            if (dreg)
+                predict_acq_tc_kernel<true><<<grid, PNT, kPredictSmemBytesTc, stream>>>(P);
+            else
+                predict_acq_tc_kernel<false><<<grid, PNT, kPredictSmemBytesTc, stream>>>(P);
+        } else if (predict_impl(g0->precision) == PREDICT_IMPL_DMMA) {
             if (dreg)
                 predict_acq_kernel<PREDICT_IMPL_DMMA, true><<<grid, PNT, kPredictSmemBytesDmma, stream>>>(P);
             else

@@ -22,6 +22,7 @@
 // independent of the grid size.
 #pragma once
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace b200bo {
 
@@ -31,6 +32,7 @@ struct GpDev {
     const double* alphav;  // [np]      alpha_, zero padded
     const double* ls;      // [d]       length scales (replicated when isotropic)
     const int* xform;      // [d] or nullptr
+    const uint8_t* linv_tc;  // fp32 mode: L^-1 as tf32 (hi,lo) UMMA operand images, or nullptr
     int n, np, family, nu;
     double constv, y_mean, y_std, lb, ub;
 };
@@ -61,7 +63,7 @@ constexpr int PBK_DMMA = 32;  // k-tile of the DMMA variant (one CTA barrier per
 constexpr int kPredictSmemBytesDmma = PSTAGES * PBK_DMMA * 2 * PSTR_DMMA * 8;  // 202752
 constexpr int kPredictMaxDimRegs = 16;  // candidates held in registers when d <= 16
 
-enum { PREDICT_IMPL_DFMA = 0, PREDICT_IMPL_DMMA = 1 };
+enum { PREDICT_IMPL_DFMA = 0, PREDICT_IMPL_DMMA = 1, PREDICT_IMPL_TF32 = 2 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -117,7 +119,10 @@ __device__ __forceinline__ void candidate_epilogue(const PredictParams& P, const
 // COV is a template parameter so that the covariance is branch-free straight-line code.
 constexpr int PA_CHUNK = 64;  // training rows per staged chunk
 
-template <bool DREG, int COV>
+// TC = false: K* written as fp64 [np][128] (operand of the fp64 GEMM variants).
+// TC = true : K* written as tf32 (hi, lo) pairs in the UMMA operand-image layout of tc_common.cuh
+//             ([np/32][hi|lo][16 KiB], candidate = operand row, training index = K).
+template <bool DREG, int COV, bool TC>
 __device__ __forceinline__ void predict_phase_a_impl(const PredictParams& P, const GpDev& G, long long c0,
                                                      double* __restrict__ Ks, double* smem,
                                                      double (*mu_s)[PBN]) {
@@ -198,32 +203,54 @@ __device__ __forceinline__ void predict_phase_a_impl(const PredictParams& P, con
                     }
                 }
             }
+            float hi[R], lo[R];
 #pragma unroll
             for (int q = 0; q < R; ++q) {
                 const int n = ch * PA_CHUNK + r0 + q;
                 double kv = G.constv * cov_eval<COV>(r2[q]);
                 if (n >= G.n) kv = 0.0;
-                Ks[(size_t)n * PBN + c] = kv;
+                if (TC) {
+                    hi[q] = tc::to_tf32((float)kv);
+                    lo[q] = tc::to_tf32((float)(kv - (double)hi[q]));
+                } else {
+                    Ks[(size_t)n * PBN + c] = kv;
+                }
                 mu_acc = fma(__ldg(G.alphav + n), kv, mu_acc);
+            }
+            if (TC) {
+                const int n0 = ch * PA_CHUNK + r0;  // multiple of 8: two groups of 4 consecutive k
+                uint8_t* img = reinterpret_cast<uint8_t*>(Ks) + (size_t)(n0 >> 5) * (2 * tc::kTcImgBytes);
+#pragma unroll
+                for (int h4 = 0; h4 < 2; ++h4) {
+                    const int off = tc::tc_img_offset(c, (n0 & 31) + 4 * h4);
+                    *reinterpret_cast<float4*>(img + off) =
+                        make_float4(hi[4 * h4], hi[4 * h4 + 1], hi[4 * h4 + 2], hi[4 * h4 + 3]);
+                    *reinterpret_cast<float4*>(img + tc::kTcImgBytes + off) =
+                        make_float4(lo[4 * h4], lo[4 * h4 + 1], lo[4 * h4 + 2], lo[4 * h4 + 3]);
+                }
             }
         }
         __syncthreads();  // chunk buffer free for the prefetch of chunk ch+2
     }
     cp_async_wait<0>();
     mu_s[half][c] = mu_acc;
+    if (TC) {
+        tc::fence_proxy_async_global();  // scratch images will be read by bulk async copies
+        tc::fence_proxy_async_smem();    // and the stage buffers overwritten by them
+    }
     __threadfence_block();
     __syncthreads();
 }
 
-template <bool DREG>
+template <bool DREG, bool TC = false>
 __device__ __forceinline__ void predict_phase_a(const PredictParams& P, const GpDev& G, long long c0,
                                                 double* __restrict__ Ks, double* smem,
                                                 double (*mu_s)[PBN]) {
     switch (cov_code(G.family, G.nu)) {
-        case 0: predict_phase_a_impl<DREG, 0>(P, G, c0, Ks, smem, mu_s); break;
-        case 1: predict_phase_a_impl<DREG, 1>(P, G, c0, Ks, smem, mu_s); break;
-        case 2: predict_phase_a_impl<DREG, 2>(P, G, c0, Ks, smem, mu_s); break;
-        default: predict_phase_a_impl<DREG, 3>(P, G, c0, Ks, smem, mu_s); break;
+        case 0: predict_phase_a_impl<DREG, 0, TC>(P, G, c0, Ks, smem, mu_s); break;
+        case 1: predict_phase_a_impl<DREG, 1, TC>(P, G, c0, Ks, smem, mu_s); break;
+        case 2: predict_phase_a_impl<DREG, 2, TC>(P, G, c0, Ks, smem, mu_s); break;
+        default: predict_phase_a_impl<DREG, 3, TC>(P, G, c0, Ks, smem, mu_s); break;
     }
 }
 
@@ -453,6 +480,205 @@ __global__ void __launch_bounds__(PNT, 1) predict_acq_kernel(const PredictParams
             }
             __syncthreads();
         }
+    }
+}
+
+// =======================================================================================
+// fp32 mode: the same fused kernel with the N^2 term on the 5th-generation tensor cores.
+//   V = L^-1 K*^T as 3xTF32 (a_hi*b_hi + a_hi*b_lo + a_lo*b_hi), fp32 accumulators in TMEM.
+//   K* itself, K* alpha_ (the mean) and the whole epilogue stay fp64: only the triangular product
+//   and the sum of squares run at reduced precision (north_star tolerance for this mode: 1e-3).
+// Warp roles during the GEMM phase (one CTA per SM, 256 threads, TMEM 2 x 128 columns):
+//   warp 0 / lane 0  producer: 1-D bulk async copies (TMA engine) of pre-tiled operand images
+//                    [A_hi|A_lo] (L^-1, tiled once at fit time) and [B_hi|B_lo] (written by phase A)
+//   warp 1 / lane 0  tcgen05.mma issuer: 4 k-steps x 3 products per 32-k stage, tcgen05.commit
+//                    releases the stage / publishes the accumulator
+//   warps 4..7       epilogue: tcgen05.ld of their TMEM quadrant, per-thread sum of squares
+// The operand images use the SWIZZLE_NONE K-major core-matrix layout, so a stage is a verbatim
+// 64 KiB byte copy - no tensor map, no swizzle bookkeeping.
+// =======================================================================================
+constexpr int TC_STAGES = 3;
+constexpr int TC_STAGE_BYTES = 4 * tc::kTcImgBytes;                // A_hi, A_lo, B_hi, B_lo
+constexpr int kPredictSmemBytesTc = TC_STAGES * TC_STAGE_BYTES;    // 196608
+constexpr int TC_TMEM_COLS = 256;                                  // two 128-column accumulators
+
+template <bool DREG>
+__global__ void __launch_bounds__(PNT, 1) predict_acq_tc_kernel(const PredictParams P) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double mu_s[2][PBN];
+    __shared__ double base_s[PBN];
+    __shared__ double prod_s[PBN];
+    __shared__ double red_s[4][PBN];
+    __shared__ uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], accfull_bar[2], accempty_bar[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t* stage_mem = reinterpret_cast<uint8_t*>(smem);
+    double* Ks = P.scratch + (long long)blockIdx.x * P.scratch_stride;  // holds the B images (bytes)
+    const long long ntiles = (P.m + PBN - 1) / PBN;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            tc::mbar_init(&full_bar[s], 1);
+            tc::mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            tc::mbar_init(&accfull_bar[b], 1);
+            tc::mbar_init(&accempty_bar[b], 4);
+        }
+        tc::mbar_fence_init();
+    }
+    if (warp == 1) tc::tmem_alloc(&tmem_base_s, TC_TMEM_COLS);
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t idesc = tc::umma_idesc_tf32(128, 128);
+
+    uint32_t stage_it = 0;  // stages filled / consumed so far (producer and MMA thread count alike)
+    uint32_t acc_it = 0;    // accumulator buffers produced / drained so far
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long c0 = tile * PBN;
+        for (int g = 0; g < P.n_gps; ++g) {
+            const GpDev& G = P.gp[g];
+            predict_phase_a<DREG, true>(P, G, c0, Ks, smem, mu_s);
+            const int nb = G.np / PBM;
+            const int nkt_row = G.np / tc::kTcK;  // images per row block in the A array
+            const uint8_t* Bimg = reinterpret_cast<const uint8_t*>(Ks);
+
+            if (warp == 0) {
+                if (lane == 0) {
+                    uint32_t it = stage_it;
+                    for (int ib = 0; ib < nb; ++ib) {
+                        const int nkt = (ib + 1) * (PBM / tc::kTcK);
+                        const uint8_t* Aimg = G.linv_tc + (size_t)ib * nkt_row * (2 * tc::kTcImgBytes);
+                        for (int kt = 0; kt < nkt; ++kt, ++it) {
+                            const int s = it % TC_STAGES;
+                            tc::mbar_wait(&empty_bar[s], ((it / TC_STAGES) & 1) ^ 1);
+                            tc::mbar_arrive_expect_tx(&full_bar[s], TC_STAGE_BYTES);
+                            uint8_t* dst = stage_mem + (size_t)s * TC_STAGE_BYTES;
+                            tc::bulk_g2s(dst, Aimg + (size_t)kt * (2 * tc::kTcImgBytes), 2 * tc::kTcImgBytes,
+                                         &full_bar[s]);
+                            tc::bulk_g2s(dst + 2 * tc::kTcImgBytes, Bimg + (size_t)kt * (2 * tc::kTcImgBytes),
+                                         2 * tc::kTcImgBytes, &full_bar[s]);
+                        }
+                    }
+                }
+            } else if (warp == 1) {
+                if (lane == 0) {
+                    uint32_t it = stage_it, ai = acc_it;
+                    for (int ib = 0; ib < nb; ++ib, ++ai) {
+                        const int nkt = (ib + 1) * (PBM / tc::kTcK);
+                        const uint32_t buf = ai & 1;
+                        tc::mbar_wait(&accempty_bar[buf], ((ai >> 1) & 1) ^ 1);
+                        tc::tc_fence_after_sync();
+                        const uint32_t d_tmem = tmem_base + buf * 128;
+                        for (int kt = 0; kt < nkt; ++kt, ++it) {
+                            const int s = it % TC_STAGES;
+                            tc::mbar_wait(&full_bar[s], (it / TC_STAGES) & 1);
+                            tc::tc_fence_after_sync();
+                            const uint32_t base = tc::smem_u32(stage_mem + (size_t)s * TC_STAGE_BYTES);
+#pragma unroll
+                            for (int j = 0; j < tc::kTcK / 8; ++j) {
+                                const uint32_t koff = j * 2 * tc::kTcLBO;
+                                const uint64_t a_hi = tc::umma_desc_kmajor_noswz(base + koff, tc::kTcLBO, tc::kTcSBO);
+                                const uint64_t a_lo = tc::umma_desc_kmajor_noswz(base + tc::kTcImgBytes + koff,
+                                                                                 tc::kTcLBO, tc::kTcSBO);
+                                const uint64_t b_hi = tc::umma_desc_kmajor_noswz(base + 2 * tc::kTcImgBytes + koff,
+                                                                                 tc::kTcLBO, tc::kTcSBO);
+                                const uint64_t b_lo = tc::umma_desc_kmajor_noswz(base + 3 * tc::kTcImgBytes + koff,
+                                                                                 tc::kTcLBO, tc::kTcSBO);
+                                tc::umma_tf32(d_tmem, a_hi, b_hi, idesc, (kt | j) ? 1u : 0u);
+                                tc::umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+                                tc::umma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
+                            }
+                            tc::umma_commit(&empty_bar[s]);
+                        }
+                        tc::umma_commit(&accfull_bar[buf]);
+                    }
+                }
+            }
+            float csq[PBN];
+            if (warp >= 4) {
+                const int q = warp & 3;
+#pragma unroll
+                for (int j = 0; j < PBN; ++j) csq[j] = 0.f;
+                uint32_t ai = acc_it;
+                for (int ib = 0; ib < nb; ++ib, ++ai) {
+                    const uint32_t buf = ai & 1;
+                    tc::mbar_wait(&accfull_bar[buf], (ai >> 1) & 1);
+                    tc::tc_fence_after_sync();
+                    const uint32_t taddr = tmem_base + buf * 128 + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+                    for (int cc = 0; cc < PBN; cc += 32) {
+                        uint32_t r[32];
+                        tc::tmem_ld_32x32(taddr + cc, r);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = __uint_as_float(r[j]);
+                            csq[cc + j] = fmaf(v, v, csq[cc + j]);
+                        }
+                    }
+                    tc::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&accempty_bar[buf]);
+                }
+            }
+            // every role advanced by the same amounts
+            {
+                uint32_t stages = 0;
+                for (int ib = 0; ib < nb; ++ib) stages += (ib + 1) * (PBM / tc::kTcK);
+                stage_it += stages;
+                acc_it += nb;
+            }
+            tc::tc_fence_before_sync();
+            __syncthreads();
+            tc::tc_fence_after_sync();
+            if (warp >= 4) {
+                const int q = warp & 3;
+                // sum over the 32 rows (lanes) of this quadrant; fp64 from here on
+#pragma unroll
+                for (int j = 0; j < PBN; ++j) {
+                    double v = (double)csq[j];
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    if (lane == 0) red_s[q][j] = v;
+                }
+            }
+            __syncthreads();
+            if (tid < PBN) {
+                const int c = tid;
+                const double colsq = ((red_s[0][c] + red_s[1][c]) + red_s[2][c]) + red_s[3][c];
+                candidate_epilogue(P, G, g, mu_s[0][c] + mu_s[1][c], colsq, c0 + c, base_s[c], prod_s[c]);
+            }
+            tc::fence_proxy_async_smem();
+            __syncthreads();
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, TC_TMEM_COLS);
+}
+
+// L^-1 (fp64, row-major) -> tf32 (hi, lo) operand images [ib][kt][hi|lo][16 KiB] (lower k-tiles only)
+__global__ void __launch_bounds__(256) pretile_linv_tc_kernel(const double* __restrict__ W, int np,
+                                                              uint8_t* __restrict__ out) {
+    const int kt = blockIdx.x, ib = blockIdx.y;
+    if (kt >= (ib + 1) * (PBM / tc::kTcK)) return;
+    uint8_t* img = out + ((size_t)ib * (np / tc::kTcK) + kt) * (2 * tc::kTcImgBytes);
+    for (int idx = threadIdx.x; idx < PBM * tc::kTcK; idx += 256) {
+        const int r = idx / tc::kTcK, k = idx % tc::kTcK;
+        const double w = W[(size_t)(ib * PBM + r) * np + kt * tc::kTcK + k];
+        const float hi = tc::to_tf32((float)w);
+        const float lo = tc::to_tf32((float)(w - (double)hi));
+        const int off = tc::tc_img_offset(r, k);
+        *reinterpret_cast<float*>(img + off) = hi;
+        *reinterpret_cast<float*>(img + tc::kTcImgBytes + off) = lo;
     }
 }
 

@@ -160,18 +160,22 @@ class _Handle:
 class B200GaussianProcessRegressor(GaussianProcessRegressor):
     """GaussianProcessRegressor whose numerics run on a B200 (fp64).
 
-    Same constructor as sklearn's plus ``device`` (CUDA ordinal).  ``fit`` mirrors
+    Same constructor as sklearn's plus ``device`` (CUDA ordinal) and ``precision``: "fp64" (exact,
+    parity 1e-5, default) or "fp32" (the N^2 term of predict on tcgen05 tensor cores as 3xTF32 with
+    fp32 accumulation; fit, K*, the mean and the acquisition epilogue stay fp64; tolerance 1e-3).  ``fit`` mirrors
     SK/gaussian_process/_gpr.py:233-368 (incl. the 1 + n_restarts_optimizer L-BFGS-B runs and the
     exact RandomState draws at :328-333); ``predict`` mirrors :370-500 for return_std;
     ``log_marginal_likelihood`` mirrors :541-656.
     """
 
     def __init__(self, kernel=None, *, alpha=1e-10, optimizer="fmin_l_bfgs_b", n_restarts_optimizer=0,
-                 normalize_y=False, copy_X_train=True, n_targets=None, random_state=None, device=0):
+                 normalize_y=False, copy_X_train=True, n_targets=None, random_state=None, device=0,
+                 precision="fp64"):
         super().__init__(kernel=kernel, alpha=alpha, optimizer=optimizer,
                          n_restarts_optimizer=n_restarts_optimizer, normalize_y=normalize_y,
                          copy_X_train=copy_X_train, n_targets=n_targets, random_state=random_state)
         self.device = device
+        self.precision = precision
 
     # ---- device plumbing -----------------------------------------------------------------
     def _handle(self) -> _Handle:
@@ -211,6 +215,9 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
         rc = L.b200bo_gp_fit(h.ptr, B.as_dp(X), B.as_dp(y), X.shape[0], d, C.byref(spec),
                              float(self.alpha), int(bool(self.normalize_y)), C.byref(info))
         B.check(rc)
+        if self.precision not in ("fp64", "fp32"):
+            raise ValueError("precision must be 'fp64' or 'fp32'")
+        B.check(L.b200bo_gp_set_precision(h.ptr, B.PRECISION_FP32 if self.precision == "fp32" else B.PRECISION_FP64))
         self.__dict__["_b200_device_fitted"] = True
         self.__dict__.pop("_b200_L", None)
         self.__dict__.pop("_b200_alpha", None)

@@ -100,6 +100,15 @@ int64_t b200bo_launch_count(void);
 int b200bo_gp_create(b200bo_gp** out, int device);
 void b200bo_gp_destroy(b200bo_gp* gp);
 
+/* Arithmetic of the N^2 term (V = L^-1 K*^T and sum V^2) in the fused predict/acquisition kernel:
+ *   B200BO_PRECISION_FP64  exact fp64 (mma.sync f64 / DFMA); parity bar 1e-5 (default)
+ *   B200BO_PRECISION_FP32  "fp32 mode": 3xTF32 on tcgen05 tensor cores, fp32 accumulate in TMEM;
+ *                          K*, the mean and the acquisition epilogue stay fp64; tolerance 1e-3.
+ * A call uses the precision of gps[0].  (BASELINE configs[2]: fp32 vs fp64 tolerance.) */
+#define B200BO_PRECISION_FP64 0
+#define B200BO_PRECISION_FP32 1
+int b200bo_gp_set_precision(b200bo_gp* gp, int precision);
+
 /* Optional per-dimension input transform (wrap_kernel); xform has d entries or NULL. Must be
  * set before fit.  Replaces R/bayes_opt/parameter.py:484-487 for float/int parameters. */
 int b200bo_gp_set_transform(b200bo_gp* gp, const int32_t* xform, int d);

@@ -17,6 +17,8 @@ timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpur
 echo "== bench (dfma variant)"
 B200BO_PREDICT_IMPL=dfma timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_dfma.json 2> gpurun_out/bench_dfma.err; cat gpurun_out/bench_dfma.json; tail -n 5 gpurun_out/bench_dfma.err
 
+echo "== bench (fp32 mode on tcgen05)"
+B200BO_PREDICT_IMPL=tf32 timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_tf32.json 2> gpurun_out/bench_tf32.err; cat gpurun_out/bench_tf32.json; tail -n 5 gpurun_out/bench_tf32.err
 echo "== fit / suggest side bench"
 timeout 900 python tools/fit_bench.py > gpurun_out/fit_bench.json 2> gpurun_out/fit_bench.err; cat gpurun_out/fit_bench.json; tail -n 3 gpurun_out/fit_bench.err
 echo "== bench reference"
