@@ -206,6 +206,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp32-mode", action="store_true", help="skip the secondary fp32-mode line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -321,6 +322,26 @@ def main():
     e2e_ms, _, _, _ = timed(step_e2e, args.steps, 1)
     e2e_value = world * m * args.steps / (e2e_ms * 1e-3)
 
+    # ---- secondary line: fp32 mode (N^2 term as 3xTF32 on tcgen05), same workload ------------
+    fp32 = None
+    if not args.no_fp32_mode:
+        gp32 = bo.B200GaussianProcessRegressor(kernel=Matern(nu=2.5, length_scale=LS), alpha=ALPHA,
+                                               normalize_y=True, optimizer=None, device=local_rank,
+                                               precision="fp32")
+        gp32.fit(X, y)
+        acq32 = ei._get_acq(gp=gp32)
+        sel32 = torch.zeros((KSEEDS + 1, 2), dtype=torch.int64, device=dev)
+
+        def step_fp32(i):
+            B.check(L.b200bo_acq_eval_dev(C.byref(acq32.spec), dev_bufs[i % N_CAND_BUFFERS].data_ptr(), m, None,
+                                          None, None, KSEEDS, sel32.data_ptr(), index_base, stream.cuda_stream))
+
+        t32_ms, k32_ms, _, clocks32 = timed(step_fp32, args.steps, args.warmup)
+        stream.synchronize()
+        s32 = sel32.cpu().numpy()
+        fp32 = {"total_ms": t32_ms, "kernel_ms": float(np.mean(k32_ms)), "clocks": clocks32,
+                "argmin_index": int(s32[0, 1]), "argmin_value": float(s32.view(np.float64)[0, 0])}
+
     if rank == 0:
         peaks = {}
         try:
@@ -363,6 +384,23 @@ def main():
             "fit_seconds_fixed_theta": fit_s,
             "result": {"argmin_index": best_idx, "argmin_value": best_val},
         })
+        if fp32 is not None:
+            tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0
+            v32 = world * m * args.steps / (fp32["total_ms"] * 1e-3)
+            executed = 3.0 * N_TRAIN * N_TRAIN * m / (fp32["kernel_ms"] * 1e-3) / 1e12  # 3 TF32 products / MAC pair
+            line["fp32_mode"] = {
+                "value": v32, "unit": "candidates/s", "dtype": "tf32x3 (fp32 accumulate in TMEM); K*, mean, "
+                "epilogue fp64", "tolerance": "1e-3 rel on the predictive variance (+1e-4 s_y^2)",
+                "kernel": "predict_acq_tc_kernel (tcgen05.mma kind::tf32, bulk-copy producer, TMEM epilogue)",
+                "kernel_ms": fp32["kernel_ms"], "clocks": fp32["clocks"],
+                "roofline": {"bound": "tensor", "achieved": executed, "peak": tf32_peak, "unit": "TFLOP/s",
+                             "frac": executed / tf32_peak,
+                             "note": "executed TF32 tensor flops (3 products per useful multiply-add); dense TF32 "
+                                     "peak taken as half the measured bf16 peak of MEASURED_PEAKS.json",
+                             "useful_tflops": flops / (fp32["kernel_ms"] * 1e-3) / 1e12},
+                "argmin_matches_fp64": fp32["argmin_index"] == best_idx,
+                "argmin_value": fp32["argmin_value"],
+            }
         if world == 1 and not args.no_cpu_baseline:
             v, secs = cpu_reference_rate(X, y, 1 << 15)
             line["cpu_baseline"] = {
