@@ -52,4 +52,30 @@ for n, d in [(1024, 8), (4096, 16)]:
                              lml_grad_eval_s=t_lml, suggest_nofit_s=t_sug,
                              acq_call_17pts_ms=1e3 * t_stencil, acq_call_1pt_ms=1e3 * t_single,
                              launches=int(L.b200bo_launch_count() - l0))
+# BASELINE configs[0]: README 2-D function, N=25, UCB - complete suggest() incl. the 6-start fit
+def black_box(x, y):
+    return -(x**2) - (y - 1) ** 2 + 1
+
+
+space = bo.TargetSpace(black_box, {"x": (2, 4), "y": (-3, 3)})
+rs = np.random.RandomState(1)
+for _ in range(25):
+    space.probe(space.random_sample(random_state=rs))
+gp = bo.B200GaussianProcessRegressor(kernel=Matern(nu=2.5), alpha=1e-6, normalize_y=True,
+                                     n_restarts_optimizer=5, random_state=rs)
+ucb = bo.UpperConfidenceBound(kappa=2.576)
+ucb.suggest(gp, space, random_state=rs)
+t0 = time.perf_counter()
+for _ in range(3):
+    ucb.suggest(gp, space, random_state=rs)
+out["c1_readme_n25"] = dict(suggest_with_fit_s=(time.perf_counter() - t0) / 3)
+try:
+    from sklearn.gaussian_process import GaussianProcessRegressor as SkGPR
+
+    skgp = SkGPR(kernel=Matern(nu=2.5), alpha=1e-6, normalize_y=True, n_restarts_optimizer=5, random_state=rs)
+    t0 = time.perf_counter()
+    skgp.fit(space.params, space.target)
+    out["c1_readme_n25"]["sklearn_fit_only_s"] = time.perf_counter() - t0
+except Exception:
+    pass
 print(json.dumps(out))
