@@ -22,8 +22,8 @@ PRECISION_FP64, PRECISION_FP32 = 0, 1
 EXPORTS = [
     "b200bo_version", "b200bo_last_error", "b200bo_device_count", "b200bo_launch_count",
     "b200bo_gp_create", "b200bo_gp_destroy", "b200bo_gp_set_precision", "b200bo_gp_set_transform", "b200bo_gp_fit",
-    "b200bo_gp_set_data", "b200bo_gp_lml", "b200bo_gp_get", "b200bo_gp_n", "b200bo_gp_dim",
-    "b200bo_gp_predict", "b200bo_acq_eval", "b200bo_acq_argmin_topk", "b200bo_acq_eval_dev",
+    "b200bo_gp_set_data", "b200bo_gp_append", "b200bo_gp_lml", "b200bo_gp_get", "b200bo_gp_n", "b200bo_gp_dim",
+    "b200bo_gp_predict", "b200bo_gp_predict_cov", "b200bo_acq_eval", "b200bo_acq_argmin_topk", "b200bo_acq_eval_dev",
     "b200bo_last_kernel_ms",
 ]
 
@@ -77,12 +77,14 @@ def lib():
     L.b200bo_gp_fit.argtypes = [C.c_void_p, dp, dp, C.c_int64, C.c_int, C.POINTER(KernelSpec),
                                 C.c_double, C.c_int, i64p]
     L.b200bo_gp_set_data.argtypes = [C.c_void_p, dp, dp, C.c_int64, C.c_int, C.c_int]
+    L.b200bo_gp_append.argtypes = [C.c_void_p, dp, C.c_double, i64p]
     L.b200bo_gp_lml.argtypes = [C.c_void_p, C.POINTER(KernelSpec), C.c_double, C.c_int, dp, dp]
     L.b200bo_gp_get.argtypes = [C.c_void_p, C.c_int, dp, C.c_int64]
     L.b200bo_gp_n.argtypes = [C.c_void_p]
     L.b200bo_gp_n.restype = C.c_int64
     L.b200bo_gp_dim.argtypes = [C.c_void_p]
     L.b200bo_gp_predict.argtypes = [C.c_void_p, dp, C.c_int64, dp, dp, i64p]
+    L.b200bo_gp_predict_cov.argtypes = [C.c_void_p, dp, C.c_int64, dp, dp]
     L.b200bo_acq_eval.argtypes = [C.POINTER(AcqSpec), dp, C.c_int64, dp]
     L.b200bo_acq_argmin_topk.argtypes = [C.POINTER(AcqSpec), dp, C.c_int64, C.c_int, dp, i64p, dp,
                                          i64p, dp]

@@ -81,6 +81,14 @@ class FusedAcquisition:
         x = B.c_f64(np.asarray(x, dtype=np.float64).reshape(-1, self.dim))
         if not np.isfinite(x).all():  # sklearn's predict raises the same way (validate_data)
             raise ValueError("Input X contains NaN or infinity.")
+        # kernels with a host-side input transform (categorical one-hot): every GP of the call must
+        # see the same transformed batch, as in the reference where they share space.kernel_transform
+        modes = [g.__dict__.get("_b200_xform", ("device", None)) for g in self._keep]
+        host = [a for m, a in modes if m == "host"]
+        if host:
+            if len(host) != len(modes) or any(h is not host[0] for h in host):
+                raise NotImplementedError("GPs of one acquisition call use different host-side input transforms")
+            x = self._keep[0]._device_candidates(x)
         return x
 
     def __call__(self, x):

@@ -77,6 +77,8 @@ struct b200bo_gp {
     double constv = 1.0, jitter = 0.0;
     double y_mean = 0.0, y_std = 1.0;
     std::vector<double> y_norm;  // host copy of normalised targets (n)
+    std::vector<double> y_raw;   // host copy of the raw targets (n)
+    bool normalize = false;
     std::vector<int> xform;      // host copy (d) or empty
     DevBuf X, Xs, y, K, L, W, WT, T, alphav, v1, v2, ls, xf, info, part;
     // predict-side scratch (used when this handle is gps[0] of a call)
@@ -87,6 +89,7 @@ struct b200bo_gp {
     // fp32 mode: L^-1 as tf32 (hi,lo) UMMA operand images (built on first use after a fit)
     DevBuf tc_linv;
     bool tc_valid = false;
+    DevBuf cov_xc, cov_kst, cov_v, cov_c, cov_out, cov_mu;  // predict(return_cov=True) scratch
     int precision = B200BO_PRECISION_FP64;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -152,7 +155,7 @@ extern "C" void b200bo_gp_destroy(b200bo_gp* gp) {
                       &gp->alphav, &gp->v1, &gp->v2, &gp->ls, &gp->xf, &gp->info, &gp->part,
                       &gp->pscratch, &gp->xc, &gp->out_acq, &gp->out_mu, &gp->out_sd, &gp->sel,
                       &gp->clamp, &gp->s_ksm, &gp->s_partial, &gp->s_mupart, &gp->s_unit, &gp->s_rb,
-                      &gp->tc_linv};
+                      &gp->tc_linv, &gp->cov_xc, &gp->cov_kst, &gp->cov_v, &gp->cov_c, &gp->cov_out, &gp->cov_mu};
     for (DevBuf* b : bufs) b->release();
     if (gp->ev0) cudaEventDestroy(gp->ev0);
     if (gp->ev1) cudaEventDestroy(gp->ev1);
@@ -208,6 +211,8 @@ extern "C" int b200bo_gp_set_data(b200bo_gp* gp, const double* X, const double* 
     // a compensated sum so the result is the correctly rounded mean / population std.
     double mean = 0.0, sd = 1.0;
     gp->y_norm.assign(y, y + n);
+    gp->y_raw.assign(y, y + n);
+    gp->normalize = normalize_y != 0;
     if (normalize_y) {
         long double s = 0.0L;
         for (int64_t i = 0; i < n; ++i) s += y[i];
@@ -224,7 +229,7 @@ extern "C" int b200bo_gp_set_data(b200bo_gp* gp, const double* X, const double* 
     gp->y_mean = mean;
     gp->y_std = sd;
     int rc;
-    if ((rc = gp->X.reserve(sizeof(double) * n * d))) return rc;
+    if ((rc = gp->X.reserve(sizeof(double) * np * d))) return rc;
     if ((rc = gp->Xs.reserve(sizeof(double) * np * d))) return rc;
     if ((rc = gp->y.reserve(sizeof(double) * np))) return rc;
     if ((rc = gp->alphav.reserve(sizeof(double) * np))) return rc;
@@ -233,6 +238,7 @@ extern "C" int b200bo_gp_set_data(b200bo_gp* gp, const double* X, const double* 
     if ((rc = gp->ls.reserve(sizeof(double) * B200BO_MAX_DIM))) return rc;
     if ((rc = gp->xf.reserve(sizeof(int) * B200BO_MAX_DIM))) return rc;
     if ((rc = gp->info.reserve(sizeof(int)))) return rc;
+    if ((rc = gp->part.reserve(sizeof(double) * 64))) return rc;
     if ((rc = gp->K.reserve(sizeof(double) * np * np))) return rc;
     if ((rc = gp->L.reserve(sizeof(double) * np * np))) return rc;
     if ((rc = gp->W.reserve(sizeof(double) * np * np))) return rc;
@@ -415,6 +421,72 @@ extern "C" int b200bo_gp_fit(b200bo_gp* gp, const double* X, const double* y, in
     gp->constv = kern->const_value;
     gp->jitter = alpha;
     gp->fitted = true;
+    return B200BO_OK;
+}
+
+// Append one training point at the hyper-parameters of the last fit, O(N^2).
+// Falls outside the padded capacity (n == np) -> B200BO_ERR_STATE: the caller refits from scratch.
+extern "C" int b200bo_gp_append(b200bo_gp* gp, const double* x_new, double y_new, int64_t* info) {
+    if (!gp || !x_new) return set_err(B200BO_ERR_ARG, "NULL argument");
+    if (!gp->fitted) return set_err(B200BO_ERR_STATE, "GP handle is not fitted");
+    if (gp->n >= gp->np) return set_err(B200BO_ERR_STATE, "no padding slack left (n == np): refit");
+    CU(cudaSetDevice(gp->device));
+    const int n = (int)gp->n, np = gp->np, d = gp->d;
+    if (info) *info = 0;
+    int rc;
+    if ((rc = gp->xc.reserve(sizeof(double) * B200BO_MAX_DIM))) return rc;
+    CU(cudaMemcpy(gp->xc.p, x_new, sizeof(double) * d, cudaMemcpyHostToDevice));
+    CU(cudaMemset(gp->info.p, 0, sizeof(int)));
+    const int* xf = gp->xform.empty() ? nullptr : gp->xf.as<int>();
+    double* kvec = gp->v1.as<double>();
+    double* lvec = gp->v2.as<double>();
+    double* tvec = gp->alphav.as<double>();  // alpha_ is recomputed below; reuse as scratch
+    if (n > 0) {
+        append_krow_kernel<<<(n + 127) / 128, 128>>>(gp->xc.as<double>(), gp->ls.as<double>(), xf, gp->Xs.as<double>(),
+                                                     gp->X.as<double>(), kvec, n, d, gp->family, gp->nu, gp->constv);
+        const int wpb = 8;
+        dim3 blk(32 * wpb), grd((n + wpb - 1) / wpb);
+        gemv_rows_kernel<<<grd, blk>>>(gp->W.as<double>(), np, kvec, lvec, n, n, 1);   // l = W k
+        append_rows_kernel<<<1, 256>>>(gp->K.as<double>(), gp->L.as<double>(), kvec, lvec, n, np,
+                                       gp->constv + gp->jitter, gp->info.as<int>(), gp->part.as<double>());
+        gemv_rows_kernel<<<grd, blk>>>(gp->WT.as<double>(), np, lvec, tvec, n, n, 2);  // t = W^T l
+        for (int i = 0; i < 4; ++i) LAUNCHED();
+    }
+    int finfo = 0;
+    CU(cudaMemcpy(&finfo, gp->info.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (finfo != 0) {
+        gp->fitted = false;  // row n of K/L is garbage now
+        if (info) *info = finfo;
+        return set_err(B200BO_ERR_NOT_PD, "%d-th leading minor of the array is not positive definite", finfo);
+    }
+    append_winv_kernel<<<(n + 1 + 127) / 128, 128>>>(gp->W.as<double>(), gp->WT.as<double>(), tvec,
+                                                     gp->part.as<double>(), n, np);
+    LAUNCHED();
+    // targets: new normalisation statistics, alpha_ = K^-1 y
+    gp->y_raw.push_back(y_new);
+    const int64_t nn = n + 1;
+    gp->y_norm = gp->y_raw;
+    double mean = 0.0, sd = 1.0;
+    if (gp->normalize) {
+        long double s = 0.0L;
+        for (int64_t i = 0; i < nn; ++i) s += gp->y_raw[i];
+        mean = (double)(s / (long double)nn);
+        long double q = 0.0L;
+        for (int64_t i = 0; i < nn; ++i) {
+            const long double t = (long double)gp->y_raw[i] - (long double)mean;
+            q += t * t;
+        }
+        sd = (double)sqrtl(q / (long double)nn);
+        if (sd == 0.0) sd = 1.0;
+        for (int64_t i = 0; i < nn; ++i) gp->y_norm[i] = (gp->y_raw[i] - mean) / sd;
+    }
+    gp->y_mean = mean;
+    gp->y_std = sd;
+    CU(cudaMemcpy(gp->y.p, gp->y_norm.data(), sizeof(double) * nn, cudaMemcpyHostToDevice));
+    gp->n = nn;
+    gp->tc_valid = false;
+    if ((rc = solve_alpha(gp))) return rc;
+    CU(cudaDeviceSynchronize());
     return B200BO_OK;
 }
 
@@ -767,6 +839,54 @@ extern "C" int b200bo_gp_predict(b200bo_gp* gp, const double* Xc, int64_t m, dou
     spec.n_gps = 1;
     spec.gps[0] = gp;
     return run_host(&spec, Xc, m, nullptr, mu, sd, 0, nullptr, n_clamped);
+}
+
+extern "C" int b200bo_gp_predict_cov(b200bo_gp* gp, const double* Xc, int64_t m, double* mu, double* cov) {
+    if (!gp || !Xc || !mu || !cov) return set_err(B200BO_ERR_ARG, "NULL argument");
+    if (!gp->fitted) return set_err(B200BO_ERR_STATE, "GP handle is not fitted");
+    if (m <= 0 || m > 16384) return set_err(B200BO_ERR_ARG, "return_cov supports 1 <= m <= 16384 (m=%lld)", (long long)m);
+    CU(cudaSetDevice(gp->device));
+    const int n = (int)gp->n, np = gp->np, d = gp->d, mi = (int)m, mp = round_up(m, 64);
+    int rc;
+    if ((rc = gp->cov_xc.reserve(sizeof(double) * (size_t)mp * d))) return rc;
+    if ((rc = gp->cov_kst.reserve(sizeof(double) * (size_t)np * mp))) return rc;
+    if ((rc = gp->cov_v.reserve(sizeof(double) * (size_t)np * mp))) return rc;
+    if ((rc = gp->cov_c.reserve(sizeof(double) * (size_t)mp * mp))) return rc;
+    if ((rc = gp->cov_out.reserve(sizeof(double) * (size_t)mi * mi))) return rc;
+    if ((rc = gp->cov_mu.reserve(sizeof(double) * (size_t)mp))) return rc;
+    if ((rc = gp->xc.reserve(sizeof(double) * (size_t)mi * d))) return rc;
+    CU(cudaMemcpy(gp->xc.p, Xc, sizeof(double) * (size_t)mi * d, cudaMemcpyHostToDevice));
+    const int* xf = gp->xform.empty() ? nullptr : gp->xf.as<int>();
+    {
+        const long long tot = (long long)mp * d;
+        scale_xc_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(gp->xc.as<double>(), gp->ls.as<double>(), xf,
+                                                                gp->cov_xc.as<double>(), mi, mp, d);
+        dim3 blk(32, 8), grd((mp + 31) / 32, (np + 7) / 8);
+        kcross_kernel<<<grd, blk>>>(gp->Xs.as<double>(), gp->cov_xc.as<double>(), gp->cov_kst.as<double>(), n, np,
+                                    mi, mp, d, gp->family, gp->nu, gp->constv);
+        cross_mean_kernel<<<(mi + 127) / 128, 128>>>(gp->cov_kst.as<double>(), gp->alphav.as<double>(),
+                                                     gp->cov_mu.as<double>(), np, mi, mp, gp->y_mean, gp->y_std);
+        LAUNCHED();
+        LAUNCHED();
+        LAUNCHED();
+    }
+    // V = L^-1 K*^T  (np x mp) ; VtV = V^T V (mp x mp)
+    if ((rc = gemm<false, false>(np, mp, np, 1.0, gp->W.as<double>(), np, 0, gp->cov_kst.as<double>(), mp, 0, 0.0,
+                                 gp->cov_v.as<double>(), mp, 0, 1, 0, 1)))
+        return rc;
+    if ((rc = gemm<true, false>(mp, mp, np, 1.0, gp->cov_v.as<double>(), mp, 0, gp->cov_v.as<double>(), mp, 0, 0.0,
+                                gp->cov_c.as<double>(), mp, 0, 1, 0, 0)))
+        return rc;
+    {
+        dim3 blk(32, 8), grd((mi + 31) / 32, (mi + 7) / 8);
+        cov_finish_kernel<<<grd, blk>>>(gp->cov_xc.as<double>(), gp->cov_c.as<double>(), mp, gp->cov_out.as<double>(),
+                                        mi, d, gp->family, gp->nu, gp->constv, gp->y_std);
+        LAUNCHED();
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(mu, gp->cov_mu.p, sizeof(double) * (size_t)mi, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(cov, gp->cov_out.p, sizeof(double) * (size_t)mi * mi, cudaMemcpyDeviceToHost));
+    return B200BO_OK;
 }
 
 extern "C" int b200bo_acq_eval(const b200bo_acq* spec, const double* Xc, int64_t m, double* acq_neg) {

@@ -258,6 +258,149 @@ __global__ void axpy1_kernel(double* __restrict__ a, const double* __restrict__ 
 // Each CTA reduces a 16x16 patch of (i,j) pairs in a fixed order and writes its partial
 // sums to part[block][p]; the host adds the partials in index order (deterministic).
 // ---------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------
+// predict(return_cov=True) helpers (SK/gaussian_process/_gpr.py:464-475)
+// ---------------------------------------------------------------------------------------
+// Xcs = transform(Xc)/length_scale, rows >= m zero
+__global__ void scale_xc_kernel(const double* __restrict__ Xc, const double* __restrict__ ls,
+                                const int* __restrict__ xform, double* __restrict__ Xcs, int m, int mp, int d) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)mp * d) return;
+    const int i = (int)(idx / d), j = (int)(idx % d);
+    double v = 0.0;
+    if (i < m) {
+        v = Xc[idx];
+        if (xform && xform[j] == B200BO_XFORM_ROUND) v = rint(v);
+        v = v / ls[j];
+    }
+    Xcs[idx] = v;
+}
+// Kst[k][c] = const * cov(Xs[k], Xcs[c])  (np x mp, zero for padded rows/columns)
+__global__ void kcross_kernel(const double* __restrict__ Xs, const double* __restrict__ Xcs,
+                              double* __restrict__ Kst, int n, int np, int m, int mp, int d, int family, int nu,
+                              double constv) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y * blockDim.y + threadIdx.y;
+    if (k >= np || c >= mp) return;
+    double v = 0.0;
+    if (k < n && c < m) {
+        const double* a = Xcs + (size_t)c * d;
+        const double* b = Xs + (size_t)k * d;
+        double r2 = 0.0;
+        for (int t = 0; t < d; ++t) {
+            const double df = a[t] - b[t];
+            r2 = fma(df, df, r2);
+        }
+        v = constv * cov_from_r2(r2, family, nu);
+    }
+    Kst[(size_t)k * mp + c] = v;
+}
+// mu[c] = y_std * sum_k alpha[k] Kst[k][c] + y_mean
+__global__ void cross_mean_kernel(const double* __restrict__ Kst, const double* __restrict__ alphav,
+                                  double* __restrict__ mu, int np, int m, int mp, double y_mean, double y_std) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    double s = 0.0;
+    for (int k = 0; k < np; ++k) s = fma(alphav[k], Kst[(size_t)k * mp + c], s);
+    mu[c] = y_std * s + y_mean;
+}
+// cov[i][j] = (k(x_i, x_j) - (V^T V)[i][j]) * y_std^2   (m x m, contiguous)
+__global__ void cov_finish_kernel(const double* __restrict__ Xcs, const double* __restrict__ VtV, int ldv,
+                                  double* __restrict__ cov, int m, int d, int family, int nu, double constv,
+                                  double y_std) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= m || j >= m) return;
+    double kv;
+    if (i == j) {
+        kv = constv;
+    } else {
+        const double* a = Xcs + (size_t)min(i, j) * d;
+        const double* b = Xcs + (size_t)max(i, j) * d;
+        double r2 = 0.0;
+        for (int t = 0; t < d; ++t) {
+            const double df = a[t] - b[t];
+            r2 += df * df;
+        }
+        kv = constv * cov_from_r2(r2, family, nu);
+    }
+    cov[(size_t)i * m + j] = (kv - VtV[(size_t)i * ldv + j]) * (y_std * y_std);
+}
+
+// ---------------------------------------------------------------------------------------
+// Incremental factor update at fixed hyper-parameters: one training point
+// is appended in O(N^2): new row of K, of L (l = L^-1 k, pivot sqrt(c+alpha-|l|^2)) and of L^-1.
+// ---------------------------------------------------------------------------------------
+// Xs[n] = transform(x)/ls ; kvec[i] = const*cov(Xs[i], Xs[n]) for i < n
+__global__ void append_krow_kernel(const double* __restrict__ x_new, const double* __restrict__ ls,
+                                   const int* __restrict__ xform, double* __restrict__ Xs, double* __restrict__ X,
+                                   double* __restrict__ kvec, int n, int d, int family, int nu, double constv) {
+    __shared__ double xs[B200BO_MAX_DIM];
+    if (threadIdx.x < d) {
+        double v = x_new[threadIdx.x];
+        if (blockIdx.x == 0) X[(size_t)n * d + threadIdx.x] = v;
+        if (xform && xform[threadIdx.x] == B200BO_XFORM_ROUND) v = rint(v);
+        v = v / ls[threadIdx.x];
+        xs[threadIdx.x] = v;
+        if (blockIdx.x == 0) Xs[(size_t)n * d + threadIdx.x] = v;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* a = Xs + (size_t)i * d;
+    double r2 = 0.0;
+    for (int t = 0; t < d; ++t) {
+        const double df = a[t] - xs[t];
+        r2 += df * df;
+    }
+    kvec[i] = constv * cov_from_r2(r2, family, nu);
+}
+// write row/column n of K, row n of L; pivot check.  lvec = L^-1[0:n,0:n] kvec.
+__global__ void append_rows_kernel(double* __restrict__ K, double* __restrict__ L, const double* __restrict__ kvec,
+                                   const double* __restrict__ lvec, int n, int np, double diag, int* info,
+                                   double* __restrict__ pivot_out) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const double l = lvec[i], k = kvec[i];
+        s = fma(l, l, s);
+        K[(size_t)n * np + i] = k;
+        K[(size_t)i * np + n] = k;
+        L[(size_t)n * np + i] = l;
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int t = 128; t > 0; t >>= 1) {
+        if (threadIdx.x < t) red[threadIdx.x] += red[threadIdx.x + t];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double piv = diag - red[0];
+        if (!(piv > 0.0)) {
+            *info = n + 1;
+            piv = 1.0;
+        }
+        const double lnn = sqrt(piv);
+        K[(size_t)n * np + n] = diag;
+        L[(size_t)n * np + n] = lnn;
+        *pivot_out = lnn;
+    }
+}
+// row n of W = L^-1 and column n of WT:  W[n][j] = -(1/l_nn) * t[j], t = W[0:n,0:n]^T lvec ; W[n][n] = 1/l_nn
+__global__ void append_winv_kernel(double* __restrict__ W, double* __restrict__ WT, const double* __restrict__ tvec,
+                                   const double* __restrict__ pivot, int n, int np) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const double inv = 1.0 / *pivot;
+    if (j < n) {
+        const double w = -inv * tvec[j];
+        W[(size_t)n * np + j] = w;
+        WT[(size_t)j * np + n] = w;
+    } else if (j == n) {
+        W[(size_t)n * np + n] = inv;
+        WT[(size_t)n * np + n] = inv;
+    }
+}
+
 constexpr int kMaxTheta = B200BO_MAX_DIM + 1;
 
 __global__ void __launch_bounds__(256)

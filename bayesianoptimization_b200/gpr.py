@@ -141,6 +141,31 @@ def probe_transform(kernel, d):
     return None if not codes.any() else codes
 
 
+def resolve_transform(kernel, d):
+    """How the kernel's input transform is applied:
+      ("device", codes|None)  per-dimension identity / np.round, done inside the CUDA kernels;
+      ("host", fn)            any other transform (e.g. the reference's categorical one-hot, which is
+                              batch-dependent: R/bayes_opt/parameter.py:434-449) - the opaque Python
+                              callable is applied to the batch on the host exactly where the reference
+                              applies it (WrappedKernel.__call__, parameter.py:484-487) and the device
+                              sees the transformed coordinates."""
+    t = find_transform(kernel)
+    if t is None and isinstance(kernel, Product):
+        t = find_transform(kernel.k1) or find_transform(kernel.k2)
+    if t is None:
+        return "device", None
+    try:
+        return "device", probe_transform(kernel, d)
+    except NotImplementedError:
+        return "host", t
+
+
+def apply_transform(mode, arg, X):
+    if mode == "host":
+        return B.c_f64(np.asarray(arg(X), dtype=np.float64))
+    return X
+
+
 class _Handle:
     """Owns one b200bo_gp*."""
 
@@ -201,10 +226,12 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
 
     def _device_fit(self, ek: EngineKernel):
         h = self._handle()
-        X = B.c_f64(self.X_train_)
         y = B.c_f64(self._y_raw)
+        mode, arg = resolve_transform(self.kernel_, self.X_train_.shape[1])
+        self.__dict__["_b200_xform"] = (mode, arg)
+        X = apply_transform(mode, arg, B.c_f64(self.X_train_))
         d = X.shape[1]
-        codes = probe_transform(self.kernel_, d)
+        codes = arg if mode == "device" else None
         L = B.lib()
         if codes is not None:
             B.check(L.b200bo_gp_set_transform(h.ptr, codes.ctypes.data_as(C.POINTER(C.c_int32)), d))
@@ -218,6 +245,7 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
         if self.precision not in ("fp64", "fp32"):
             raise ValueError("precision must be 'fp64' or 'fp32'")
         B.check(L.b200bo_gp_set_precision(h.ptr, B.PRECISION_FP32 if self.precision == "fp32" else B.PRECISION_FP64))
+        self.__dict__["_b200_fit_sig"] = self._fit_signature(ek)
         self.__dict__["_b200_device_fitted"] = True
         self.__dict__.pop("_b200_L", None)
         self.__dict__.pop("_b200_alpha", None)
@@ -288,6 +316,9 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
             self._y_train_mean = np.zeros(1)
             self._y_train_std = np.ones(1)
             y_norm = y
+        prev = None
+        if self.__dict__.get("_b200_device_fitted", False) and hasattr(self, "_y_raw"):
+            prev = (self.X_train_, self._y_raw, self.__dict__.get("_b200_fit_sig"))
         self.X_train_ = X
         self.y_train_ = y_norm
         self._y_raw = y.copy()
@@ -296,11 +327,13 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
         if self.optimizer is not None and self.kernel_.n_dims > 0:
             h = self._handle()
             L = B.lib()
-            codes = probe_transform(self.kernel_, X.shape[1])
+            mode, arg = resolve_transform(self.kernel_, X.shape[1])
+            Xd = apply_transform(mode, arg, B.c_f64(X))
+            codes = arg if mode == "device" else None
             B.check(L.b200bo_gp_set_transform(
                 h.ptr, codes.ctypes.data_as(C.POINTER(C.c_int32)) if codes is not None else None,
-                X.shape[1]))
-            B.check(L.b200bo_gp_set_data(h.ptr, B.as_dp(X), B.as_dp(B.c_f64(y)), X.shape[0], X.shape[1],
+                Xd.shape[1]))
+            B.check(L.b200bo_gp_set_data(h.ptr, B.as_dp(Xd), B.as_dp(B.c_f64(y)), Xd.shape[0], Xd.shape[1],
                                          int(bool(self.normalize_y))))
 
             def obj_func(theta, eval_gradient=True):
@@ -325,9 +358,43 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
             ek = parse_kernel(self.kernel_)
             self._device_fit(ek)
         else:
-            self._device_fit(ek)
+            if not self._try_incremental(prev, X, y, ek):
+                self._device_fit(ek)
             self.log_marginal_likelihood_value_ = None  # computed on demand (costs one more factorisation)
         return self
+
+    def _try_incremental(self, prev, X, y, ek):
+        """Fixed hyper-parameters (optimizer=None) and the new training set = the previous one plus
+        appended rows: extend the device factor in O(N^2) per row instead of re-factorising
+        (SURVEY.md 8f rank 3).  Same results as a from-scratch fit to round-off."""
+        if prev is None or self.__dict__.get("_b200_handle") is None:
+            return False
+        Xp, yp, sig = prev
+        k = X.shape[0] - Xp.shape[0]
+        if not (0 < k <= 8) or X.shape[1] != Xp.shape[1] or sig != self._fit_signature(ek):
+            return False
+        if not (np.array_equal(X[:-k], Xp) and np.array_equal(y[:-k], yp)):
+            return False
+        mode, arg = resolve_transform(self.kernel_, X.shape[1])
+        if mode != "device":
+            return False
+        L = B.lib()
+        h = self._handle()
+        for i in range(Xp.shape[0], X.shape[0]):
+            info = C.c_int64(0)
+            rc = L.b200bo_gp_append(h.ptr, B.as_dp(B.c_f64(X[i])), float(y[i]), C.byref(info))
+            if rc == B.ERR_STATE:
+                return False  # capacity exhausted: full refit
+            B.check(rc)
+        self.__dict__["_b200_xform"] = (mode, arg)
+        self.__dict__["_b200_device_fitted"] = True
+        self.__dict__.pop("_b200_L", None)
+        self.__dict__.pop("_b200_alpha", None)
+        return True
+
+    def _fit_signature(self, ek):
+        return (ek.family, ek.nu, ek.const_value, tuple(ek.length_scale.tolist()), float(self.alpha),
+                bool(self.normalize_y), self.precision)
 
     def _constrained_optimization(self, obj_func, initial_theta, bounds):
         """SK/gaussian_process/_gpr.py:658-674."""
@@ -368,8 +435,9 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
             kernel = self.kernel_
             kernel.theta = theta
         h = self._handle()
-        X = B.c_f64(self.X_train_)
-        codes = probe_transform(self.kernel_, X.shape[1])
+        mode, arg = resolve_transform(self.kernel_, self.X_train_.shape[1])
+        X = apply_transform(mode, arg, B.c_f64(self.X_train_))
+        codes = arg if mode == "device" else None
         L = B.lib()
         B.check(L.b200bo_gp_set_transform(
             h.ptr, codes.ctypes.data_as(C.POINTER(C.c_int32)) if codes is not None else None, X.shape[1]))
@@ -398,14 +466,17 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
             if return_std:
                 return y_mean, np.sqrt(kernel.diag(X))
             return y_mean
-        if return_cov:
-            raise NotImplementedError("predict(return_cov=True) is not on the accelerated path yet")
         if X.shape[1] != self.X_train_.shape[1]:
             raise ValueError(f"X has {X.shape[1]} features, but the GP was fitted with "
                              f"{self.X_train_.shape[1]} features.")
         self._ensure_device_fit()
-        Xc = B.c_f64(X)
+        Xc = self._device_candidates(B.c_f64(X))
         m = Xc.shape[0]
+        if return_cov:  # :464-475, device: K(X*,X*) - V^T V
+            mu = np.empty(m)
+            cov = np.empty((m, m))
+            B.check(B.lib().b200bo_gp_predict_cov(self._handle().ptr, B.as_dp(Xc), m, B.as_dp(mu), B.as_dp(cov)))
+            return mu, cov
         mu = np.empty(m)
         sd = np.empty(m) if return_std else None
         nclamp = C.c_int64(0)
@@ -416,6 +487,12 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
                 warnings.warn("Predicted variances smaller than 0. Setting those variances to 0.")
             return mu, sd
         return mu
+
+    def _device_candidates(self, X):
+        """Candidates as the device sees them (host-side transform applied when the kernel carries
+        one the CUDA kernels do not implement)."""
+        mode, arg = self.__dict__.get("_b200_xform", ("device", None))
+        return apply_transform(mode, arg, X)
 
     def sample_y(self, X, n_samples=1, random_state=0):
         raise NotImplementedError("sample_y needs return_cov; not on the accelerated path")

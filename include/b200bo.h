@@ -121,6 +121,13 @@ int b200bo_gp_set_transform(b200bo_gp* gp, const int32_t* xform, int d);
 int b200bo_gp_fit(b200bo_gp* gp, const double* X, const double* y, int64_t n, int d,
                   const b200bo_kernel* kern, double alpha, int normalize_y, int64_t* info);
 
+/* Incremental factor update (no counterpart in the reference, which always re-factorises:
+ * R/bayes_opt/acquisition.py:84, :1130-1135): append ONE training point at the hyper-parameters of
+ * the last b200bo_gp_fit in O(N^2) - new row of K, L (pivot checked) and L^-1, new y statistics and
+ * alpha_.  Results equal a from-scratch fit on the extended data to round-off.  Returns
+ * B200BO_ERR_STATE when the padded capacity is exhausted (caller refits), B200BO_ERR_NOT_PD as fit. */
+int b200bo_gp_append(b200bo_gp* gp, const double* x_new, double y_new, int64_t* info);
+
 /* Replaces GaussianProcessRegressor.log_marginal_likelihood(theta, eval_gradient)
  * (SK/gaussian_process/_gpr.py:541-656) on the training set of the last b200bo_gp_set_data /
  * b200bo_gp_fit call.  grad (nullable) receives d LML / d log(theta): [log const_value if
@@ -147,6 +154,11 @@ int b200bo_gp_dim(const b200bo_gp* gp);
  * receives the number of negative variances set to 0 (the reference warns, :485-491). */
 int b200bo_gp_predict(b200bo_gp* gp, const double* Xc, int64_t m, double* mu, double* sd,
                       int64_t* n_clamped);
+
+/* Replaces GaussianProcessRegressor.predict(X, return_cov=True) (SK/gaussian_process/_gpr.py:464-475):
+ * cov = (K(X*,X*) - V^T V) * y_std^2 with V = L^-1 K*^T.  mu: (m,), cov: (m,m) host.  1 <= m <= 16384.
+ * The only caller in the reference is BayesianOptimization.predict (R/bayes_opt/bayesian_optimization.py:238). */
+int b200bo_gp_predict_cov(b200bo_gp* gp, const double* Xc, int64_t m, double* mu, double* cov);
 
 /* Replaces the closure returned by AcquisitionFunction._get_acq (R/bayes_opt/acquisition.py:
  * 171-219) incl. ConstraintModel.predict (R/bayes_opt/constraint.py:153-221):

@@ -252,6 +252,33 @@ def case_mixed_int():
          y_max=np.float64(space.target.max()), suggestion=sug, rand_draw=space.random_sample(50, RandomState(9)))
 
 
+def case_categorical():
+    """Float + categorical parameter: the one-hot kernel transform of R/bayes_opt/parameter.py:434-449
+    (batch-dependent as written in the reference) through wrap_kernel."""
+    def f(x, c):
+        return -((x - 2.0) ** 2) + {"a": 0.0, "b": 1.0, "c": -0.5}[c]
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        space = TargetSpace(f, {"x": (0.0, 5.0), "c": ["a", "b", "c"]})
+        rs = RandomState(4)
+        for _ in range(14):
+            space.probe(space.random_sample(random_state=rs))
+        gp = GaussianProcessRegressor(
+            kernel=wrap_kernel(Matern(nu=2.5, length_scale=1.1), space.kernel_transform), alpha=1e-6,
+            normalize_y=True, optimizer=None)
+        gp.fit(space.params, space.target)
+        xt = space.random_sample(300, RandomState(8))
+        xt[:, 0] = RandomState(9).uniform(0, 5, 300)
+        xt[:, 1:] = RandomState(10).uniform(0, 1, (300, 3))
+        ucb = acquisition.UpperConfidenceBound(kappa=2.0)
+        ys = ucb._get_acq(gp=gp)(xt)
+        ys_single = np.array([ucb._get_acq(gp=gp)(xt[i])[0] for i in range(12)])
+        mu, sd = gp.predict(xt, return_std=True)
+    save("categorical_small", X=space.params, y=space.target, xt=xt, acq_ucb=ys, acq_single=ys_single,
+         mu=mu, sd=sd, X_transformed=space.kernel_transform(space.params))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     case_readme()
@@ -261,3 +288,4 @@ if __name__ == "__main__":
     case_fit_full()
     case_constant_liar()
     case_mixed_int()
+    case_categorical()

@@ -746,3 +746,75 @@ def test_fp32_mode_tcgen05_vs_oracle(bo, O, n, d, m, monkeypatch):
     assert ref[idx] <= ref.min() + 2e-3 * abs(ref.min()) + 1e-5 * s_y
     # the fp64 handle is untouched by the other handle's mode
     assert_allclose(gp64.predict(xt[:256], return_std=True)[1], sd0[:256], rtol=RTOL, atol=1e-10)
+
+
+def test_categorical_parameter_host_transform(bo, golden):
+    """Categorical parameter: the reference's one-hot kernel transform (batch-dependent as written,
+    R/bayes_opt/parameter.py:434-449) is an opaque callable -> applied on the host to each batch,
+    exactly where WrappedKernel.__call__ applies it; values must equal the reference's."""
+    from bayesianoptimization_b200.kernels import wrap_kernel
+
+    g = golden("categorical_small")
+
+    def transform(v):  # == TargetSpace.kernel_transform of {"x": float, "c": 3 categories}
+        v = np.atleast_2d(v)
+        cat = v[:, 1:]
+        res = np.zeros(cat.shape)
+        res[:, np.argmax(cat, axis=1)] = 1
+        return np.hstack([v[:, :1], res])
+
+    assert np.array_equal(transform(g["X"]), g["X_transformed"])
+    gp = make_gp(bo, wrap_kernel(Matern(nu=2.5, length_scale=1.1), transform)).fit(g["X"], g["y"])
+    mu, sd = gp.predict(g["xt"], return_std=True)
+    assert_allclose(mu, g["mu"], rtol=RTOL, atol=1e-10)
+    assert_allclose(sd, g["sd"], rtol=RTOL, atol=1e-9)
+    f = bo.UpperConfidenceBound(kappa=2.0)._get_acq(gp=gp)
+    assert_allclose(f(g["xt"]), g["acq_ucb"], rtol=RTOL, atol=1e-10)
+    assert_allclose([f(g["xt"][i])[0] for i in range(12)], g["acq_single"], rtol=RTOL, atol=1e-10)
+
+
+@pytest.mark.parametrize("n,d,m", [(50, 2, 7), (700, 5, 100), (1024, 8, 257)])
+def test_predict_return_cov_vs_sklearn(bo, n, d, m):
+    """predict(return_cov=True) (SK/gaussian_process/_gpr.py:464-475) against the live sklearn GPR."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+
+    X, y = _synth(n, d)
+    xt = np.random.RandomState(2).uniform(size=(m, d))
+    k = ConstantKernel(1.5) * Matern(nu=2.5, length_scale=0.6)
+    ref = GaussianProcessRegressor(kernel=k, alpha=1e-6, normalize_y=True, optimizer=None).fit(X, y)
+    gp = make_gp(bo, k).fit(X, y)
+    mu0, c0 = ref.predict(xt, return_cov=True)
+    mu, c = gp.predict(xt, return_cov=True)
+    assert c.shape == (m, m)
+    assert_allclose(mu, mu0, rtol=RTOL, atol=1e-10)
+    assert_allclose(c, c0, rtol=RTOL, atol=1e-9 * float(np.var(y)))
+    assert_allclose(np.sqrt(np.maximum(np.diag(c), 0)), gp.predict(xt, return_std=True)[1], rtol=1e-6, atol=1e-7)
+    with pytest.raises(RuntimeError):
+        gp.predict(xt, return_std=True, return_cov=True)
+
+
+def test_incremental_append_equals_full_fit(bo, O):
+    """Fixed theta: fitting on X[:n+k] after X[:n] extends the factor in O(N^2) per row
+    (b200bo_gp_append) and must equal a from-scratch fit, incl. across the 128-row padding edge."""
+    X, y = _synth(140, 3)
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=0.5))
+    gp.fit(X[:120], y[:120])
+    launches = bo._lib.lib().b200bo_launch_count
+    for n in (121, 124, 128, 129, 131):   # 128 -> 129 crosses the capacity: falls back to a full fit
+        l0 = launches()
+        gp.fit(X[:n], y[:n])
+        used = launches() - l0
+        st = O.fit_fixed(X[:n], y[:n], length_scale=0.5)
+        assert_allclose(gp.L_, st.L, rtol=1e-8, atol=1e-11)
+        assert_allclose(gp.alpha_, st.alpha_, rtol=1e-6, atol=1e-9)
+        xt = np.random.RandomState(n).uniform(size=(50, 3))
+        mu, sd = gp.predict(xt, return_std=True)
+        mu0, sd0 = O.predict(st, xt)
+        assert_allclose(mu, mu0, rtol=RTOL, atol=1e-10)
+        assert_allclose(sd, sd0, rtol=RTOL, atol=1e-9)
+        if n in (121, 124, 128, 131):
+            assert used < 60, (n, used)   # incremental path (a full fit at np=128/256 is > 20 launches/row...)
+    # duplicate point with alpha=0 -> not positive definite, as a full fit would report
+    gp0 = make_gp(bo, Matern(nu=2.5, length_scale=0.5), alpha=0.0, normalize_y=False).fit(X[:20], y[:20])
+    with pytest.raises(np.linalg.LinAlgError):
+        gp0.fit(np.vstack([X[:20], X[:1]]), np.append(y[:20], y[0]))
