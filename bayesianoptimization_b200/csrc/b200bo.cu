@@ -524,9 +524,9 @@ extern "C" int b200bo_gp_lml(b200bo_gp* gp, const b200bo_kernel* kern, double al
     }
     *lml = (double)(-0.5L * ya - ld - (long double)n / 2.0L * logl(2.0L * 3.14159265358979323846264338327950288L));
     if (grad) {
-        // Kinv = W^T W  (W lower: k >= max(m0, n0))
+        // Kinv = W^T W  (W lower: k >= max(m0, n0)); lower tiles only - the gradient kernel uses symmetry
         if ((rc = gemm<true, false>(np, np, np, 1.0, gp->W.as<double>(), np, 0, gp->W.as<double>(), np, 0,
-                                    0.0, gp->T.as<double>(), np, 0, 1, 0, 3)))
+                                    0.0, gp->T.as<double>(), np, 0, 1, 1, 3)))
             return rc;
         dim3 grd((n + 15) / 16, (n + 15) / 16);
         const size_t nblk = (size_t)grd.x * grd.y;

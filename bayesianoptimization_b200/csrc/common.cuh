@@ -16,6 +16,15 @@ constexpr int kPad = 128;  // training-set size is padded to a multiple of this
 // their code size hurt more than the arithmetic.  Both routines are <= 1 ulp from libm on their
 // domain (checked against numpy over 3e5 random arguments), far inside the 1e-5 parity bar.
 
+// Polynomial / reduction constants live in constant memory: an fp64 immediate costs two uniform
+// moves every time it is used, a constant-bank operand is free.
+__constant__ double kExpC[14] = {
+    1.6059043836821613e-10, 2.0876756987868100e-09, 2.5052108385441720e-08, 2.7557319223985893e-07,
+    2.7557319223985888e-06, 2.4801587301587302e-05, 1.9841269841269841e-04, 1.3888888888888889e-03,
+    8.3333333333333332e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0, 1.0};
+__constant__ double kExpR[4] = {1.4426950408889634074, -6.93147180369123816490e-01,
+                                -1.90821492927058770002e-10, 700.0};
+
 // sqrt(x) for x >= 0 (arguments below 1e-30 are treated as 1e-30: |error| <= 1e-15 absolute).
 __device__ __forceinline__ double sqrt_pos(double x) {
     const double xc = fmax(x, 1e-30);
@@ -30,24 +39,13 @@ __device__ __forceinline__ double sqrt_pos(double x) {
 
 // exp(-k) for k >= 0 (k > 700 is clamped: the result, < 1e-304, is irrelevant at fp64 scale).
 __device__ __forceinline__ double exp_neg(double k) {
-    k = fmin(k, 700.0);
-    const double n = rint(-k * 1.4426950408889634074);
-    double r = fma(n, -6.93147180369123816490e-01, -k);
-    r = fma(n, -1.90821492927058770002e-10, r);
-    double p = 1.6059043836821613e-10;               // 1/13!
-    p = fma(p, r, 2.0876756987868100e-09);           // 1/12!
-    p = fma(p, r, 2.5052108385441720e-08);           // 1/11!
-    p = fma(p, r, 2.7557319223985893e-07);           // 1/10!
-    p = fma(p, r, 2.7557319223985888e-06);           // 1/9!
-    p = fma(p, r, 2.4801587301587302e-05);           // 1/8!
-    p = fma(p, r, 1.9841269841269841e-04);           // 1/7!
-    p = fma(p, r, 1.3888888888888889e-03);           // 1/6!
-    p = fma(p, r, 8.3333333333333332e-03);           // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);           // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);           // 1/3!
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    k = fmin(k, kExpR[3]);
+    const double n = rint(-k * kExpR[0]);
+    double r = fma(n, kExpR[1], -k);
+    r = fma(n, kExpR[2], r);
+    double p = kExpC[0];  // Taylor 1/13! ... 1/0!, |r| <= ln2/2: truncation 4e-18
+#pragma unroll
+    for (int i = 1; i < 14; ++i) p = fma(p, r, kExpC[i]);
     const long long e = ((long long)n + 1023ll) << 52;  // 2^n, n in [-1010, 0]
     return p * __longlong_as_double(e);
 }

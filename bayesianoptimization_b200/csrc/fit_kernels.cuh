@@ -151,43 +151,49 @@ potrf_diag_kernel(double* A, int ld, int j0, double* Dinv, int ldd, int* info) {
         S[r][c] = A[(size_t)(j0 + r) * ld + j0 + c];
     }
     __syncthreads();
+    // right-looking, two barriers per column: every thread derives the pivot itself (the square
+    // root goes to diag[], S[k][k] keeps the pivot so late readers still see it), the first 64
+    // threads scale the column, then all 256 apply the rank-1 update to the trailing lower triangle
+    __shared__ double diag[64];
     for (int k = 0; k < 64; ++k) {
-        if (tid == 0) {
-            double piv = S[k][k];
-            if (!(piv > 0.0)) {
-                if (*info == 0) *info = j0 + k + 1;
-                piv = 1.0;
-            }
-            S[k][k] = sqrt(piv);
+        double piv = S[k][k];
+        const bool bad = !(piv > 0.0);
+        if (bad) piv = 1.0;
+        const double lkk = sqrt(piv);
+        if (tid == k) {
+            diag[k] = lkk;
+            if (bad && *info == 0) *info = j0 + k + 1;
+        } else if (tid > k && tid < 64) {
+            S[tid][k] = S[tid][k] / lkk;
         }
         __syncthreads();
-        if (tid > k && tid < 64) S[tid][k] = S[tid][k] / S[k][k];
-        __syncthreads();
-        // trailing update of the lower triangle: S[i][j] -= S[i][k]*S[j][k], k < j <= i
-        for (int idx = tid; idx < 64 * 64; idx += 256) {
-            const int i = idx >> 6, j = idx & 63;
-            if (j > k && i >= j) S[i][j] = fma(-S[i][k], S[j][k], S[i][j]);
+        const int rem = 63 - k;  // trailing block (k+1..63)^2, lower part: S[i][j] -= S[i][k]*S[j][k]
+        for (int idx = tid; idx < rem * rem; idx += 256) {
+            const int i = k + 1 + idx / rem, j = k + 1 + idx % rem;
+            if (j <= i) S[i][j] = fma(-S[i][k], S[j][k], S[i][j]);
         }
         __syncthreads();
     }
     // write factor back (zero the strict upper part of the block)
     for (int idx = tid; idx < 64 * 64; idx += 256) {
         const int r = idx >> 6, c = idx & 63;
-        A[(size_t)(j0 + r) * ld + j0 + c] = (c <= r) ? S[r][c] : 0.0;
+        A[(size_t)(j0 + r) * ld + j0 + c] = (c < r) ? S[r][c] : (c == r ? diag[r] : 0.0);
     }
-    // inverse of the lower-triangular block, one column per thread (forward substitution)
-    if (tid < 64) {
-        const int c = tid;
+    // inverse of the lower-triangular block: column c by forward substitution, 4 threads per
+    // column share each dot product (lanes 4c..4c+3, combined with two shuffles, fixed order)
+    {
+        const int c = tid >> 2, q = tid & 3;
         for (int i = 0; i < 64; ++i) {
-            double v;
-            if (i < c) {
-                v = 0.0;
-            } else {
-                double s = (i == c) ? 1.0 : 0.0;
-                for (int k = c; k < i; ++k) s = fma(-S[i][k], V[k][c], s);
-                v = s / S[i][i];
+            double part = 0.0;
+            for (int k = c + q; k < i; k += 4) part = fma(S[i][k], V[k][c], part);
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            if (q == 0) {
+                double v = 0.0;
+                if (i >= c) v = (((i == c) ? 1.0 : 0.0) - part) / diag[i];
+                V[i][c] = v;
             }
-            V[i][c] = v;
+            __syncwarp();
         }
     }
     __syncthreads();
@@ -411,12 +417,15 @@ lml_grad_kernel(const double* __restrict__ Xs, const double* __restrict__ Kinv, 
     const int i = blockIdx.y * 16 + (threadIdx.x >> 4);
     __shared__ double red[256];
     const int bid = blockIdx.y * gridDim.x + blockIdx.x;
-    const bool valid = (i < n && j < n);
+    // K^-1 and dK/dtheta are symmetric: only pairs i >= j are visited (K^-1's upper tiles are never
+    // computed) and off-diagonal pairs count twice
+    const bool valid = (i < n && j < n && j <= i);
     double w = 0.0, r2 = 0.0, kval = 0.0, gcommon = 0.0;
     const double* a = Xs + (size_t)(valid ? i : 0) * d;
     const double* b = Xs + (size_t)(valid ? j : 0) * d;
     if (valid) {
         w = alphav[i] * alphav[j] - Kinv[(size_t)i * ldk + j];
+        if (i != j) w *= 2.0;
         for (int t = 0; t < d; ++t) {
             const double df = a[t] - b[t];
             r2 += df * df;

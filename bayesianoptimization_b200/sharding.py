@@ -60,3 +60,20 @@ def allgather_selection(local_values, local_indices, k: int, device=None):
     dist.all_gather(out, rec)
     allr = torch.stack(out).cpu().numpy()
     return merge_selection(allr[:, :, 0], allr[:, :, 1].astype(np.int64), k)
+
+
+def sharded_argmin_topk(acq, x_shard, k: int, start_index: int, device=None):
+    """Multi-GPU version of AcquisitionFunction._random_sample_minimize's selection
+    (R/bayes_opt/acquisition.py:312-317): every rank evaluates its contiguous shard of the candidate
+    matrix with the fused kernel (``acq`` = FusedAcquisition on this rank's replica of the model),
+    then ONE all_gather merges the (argmin, top-k) records.  Returns global (best_idx, best_val,
+    topk_idx) - identical on every rank and identical to the single-GPU result."""
+    import numpy as np
+
+    idx, val, top = acq.argmin_topk(x_shard, k)
+    vals = np.full(k + 1, np.nan)
+    idxs = np.full(k + 1, -1, dtype=np.int64)
+    ys_top = acq(x_shard[top]) if len(top) else np.empty(0)
+    vals[0], idxs[0] = val, start_index + idx
+    vals[1:1 + len(top)], idxs[1:1 + len(top)] = ys_top, start_index + top
+    return allgather_selection(vals, idxs, k, device=device)

@@ -224,7 +224,6 @@ def main():
 
     import bayesianoptimization_b200 as bo
     from bayesianoptimization_b200 import _lib as B
-    from bayesianoptimization_b200.sharding import allgather_selection
     from sklearn.gaussian_process.kernels import Matern
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
@@ -259,9 +258,17 @@ def main():
     stream = torch.cuda.current_stream()
     index_base = rank * m
 
+    gathered = torch.zeros((world, KSEEDS + 1, 2), dtype=torch.int64, device=dev) if world > 1 else None
+
+    def exchange():
+        # the path's ONE exchange step: all_gather of the (argmin, top-k) records, 176 B per rank
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, sel)
+
     def step_device(i):
         B.check(L.b200bo_acq_eval_dev(C.byref(acq.spec), dev_bufs[i % N_CAND_BUFFERS].data_ptr(), m, None,
                                       None, None, KSEEDS, sel.data_ptr(), index_base, stream.cuda_stream))
+        exchange()
 
     xdev = torch.empty((m, D), dtype=torch.float64, device=dev)
 
@@ -271,6 +278,7 @@ def main():
         xdev.copy_(host_bufs[i % N_CAND_BUFFERS], non_blocking=True)
         B.check(L.b200bo_acq_eval_dev(C.byref(acq.spec), xdev.data_ptr(), m, None, None, None, KSEEDS,
                                       sel.data_ptr(), index_base, stream.cuda_stream))
+        exchange()
         sel_host.copy_(sel, non_blocking=True)
         stream.synchronize()
         return sel_host
@@ -310,15 +318,16 @@ def main():
     total_ms, kernel_ms, launches, clocks = timed(step_device, args.steps, args.warmup)
     value = world * m * args.steps / (total_ms * 1e-3)
 
-    # one exchange step: merge per-rank records (argmin + seeds) - outside the per-step loop it is
-    # a single all_gather of 11 x 16 B per rank
+    # merge of the gathered per-rank records (argmin + seeds) with (value, index) ordering
     stream.synchronize()
-    sel_np = sel.cpu().numpy()
-    sel_vals = sel_np.view(np.float64)[:, 0].copy()
     if world > 1:
-        best_idx, best_val, _ = allgather_selection(sel_vals, sel_np[:, 1].copy(), KSEEDS, device=dev)
+        from bayesianoptimization_b200.sharding import merge_selection
+
+        allr = gathered.cpu().numpy()
+        best_idx, best_val, _ = merge_selection(allr.view(np.float64)[:, :, 0], allr[:, :, 1], KSEEDS)
     else:
-        best_idx, best_val = int(sel_np[0, 1]), float(sel_vals[0])
+        sel_np = sel.cpu().numpy()
+        best_idx, best_val = int(sel_np[0, 1]), float(sel_np.view(np.float64)[0, 0])
 
     e2e_ms, _, _, _ = timed(step_e2e, args.steps, 1)
     e2e_value = world * m * args.steps / (e2e_ms * 1e-3)

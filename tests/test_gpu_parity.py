@@ -818,3 +818,37 @@ def test_incremental_append_equals_full_fit(bo, O):
     gp0 = make_gp(bo, Matern(nu=2.5, length_scale=0.5), alpha=0.0, normalize_y=False).fit(X[:20], y[:20])
     with pytest.raises(np.linalg.LinAlgError):
         gp0.fit(np.vstack([X[:20], X[:1]]), np.append(y[:20], y[0]))
+
+
+def test_sharded_argmin_topk_single_process_group(bo, golden):
+    """The sharded selection helper (one all_gather of (k+1) records) on a 1-rank gloo group, two
+    shards evaluated in turn: merged result == single-batch result."""
+    import socket
+
+    import torch.distributed as dist
+
+    from bayesianoptimization_b200.sharding import merge_selection, shard_range, sharded_argmin_topk
+
+    g = golden("c2s_ei")
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=0.7)).fit(g["X"], g["y"])
+    a = bo.ExpectedImprovement(xi=float(g["xi"]))
+    a.y_max = float(g["y_max"])
+    f = a._get_acq(gp=gp)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        bi, bv, top = sharded_argmin_topk(f, g["xt"], 10, 0)
+        assert bi == int(g["argmin"]) and list(top) == list(g["top10"])
+    finally:
+        dist.destroy_process_group()
+    # two shards merged by hand with the same record format
+    vals, idxs = np.full((2, 11), np.nan), np.full((2, 11), -1, dtype=np.int64)
+    for r in range(2):
+        s0, s1 = shard_range(len(g["xt"]), r, 2)
+        i, v, t = f.argmin_topk(g["xt"][s0:s1], 10)
+        vals[r, 0], idxs[r, 0] = v, s0 + i
+        vals[r, 1:1 + len(t)], idxs[r, 1:1 + len(t)] = f(g["xt"][s0:s1][t]), s0 + t
+    bi, bv, top = merge_selection(vals, idxs, 10)
+    assert bi == int(g["argmin"]) and list(top) == list(g["top10"])
