@@ -270,18 +270,20 @@ def main():
                                       None, None, KSEEDS, sel.data_ptr(), index_base, stream.cuda_stream))
         exchange()
 
-    xdev = torch.empty((m, D), dtype=torch.float64, device=dev)
+    host_np = [t.numpy() for t in host_bufs]  # numpy views of the pinned buffers
 
     def step_e2e(i):
-        # host (pinned) -> device copy of this step's candidates, fused kernel + selection,
-        # device -> host read of the (argmin, top-k) records
-        xdev.copy_(host_bufs[i % N_CAND_BUFFERS], non_blocking=True)
-        B.check(L.b200bo_acq_eval_dev(C.byref(acq.spec), xdev.data_ptr(), m, None, None, None, KSEEDS,
-                                      sel.data_ptr(), index_base, stream.cuda_stream))
-        exchange()
-        sel_host.copy_(sel, non_blocking=True)
-        stream.synchronize()
-        return sel_host
+        # the call a user of the package makes (AcquisitionFunction._random_sample_minimize does exactly
+        # this): host candidates in, (argmin, value, seed indices) out.  Inside: finite check, H2D copy
+        # of the batch from pinned host memory, fused kernel + selection, D2H of the records.
+        idx, val, top = acq.argmin_topk(host_np[i % N_CAND_BUFFERS], KSEEDS)
+        if world > 1:  # the exchange step, from host-side records
+            rec = torch.full((KSEEDS + 1, 2), -1, dtype=torch.int64)
+            rec[0, 0] = int(np.float64(val).view(np.int64))
+            rec[0, 1] = index_base + idx
+            rec[1:1 + len(top), 1] = torch.from_numpy(index_base + np.asarray(top, dtype=np.int64))
+            dist.all_gather_into_tensor(gathered, rec.to(dev))
+        return idx
 
     def barrier():
         if world > 1:
@@ -378,7 +380,8 @@ def main():
             "value": value, "ms_per_step": total_ms / args.steps,
             "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": m * D * 8,
                     "d2h_bytes_per_step": (KSEEDS + 1) * 16, "ms_per_step": e2e_ms / args.steps,
-                    "api": "b200bo_acq_eval_dev over pinned host candidates + D2H of argmin/top-k records"},
+                    "api": "FusedAcquisition.argmin_topk(host ndarray, k) - the package's public call: finite check, "
+                           "H2D of the batch from pinned host memory, fused kernel + selection, D2H of the records"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
