@@ -52,6 +52,40 @@ for n, d in [(1024, 8), (4096, 16)]:
                              lml_grad_eval_s=t_lml, suggest_nofit_s=t_sug,
                              acq_call_17pts_ms=1e3 * t_stencil, acq_call_1pt_ms=1e3 * t_single,
                              launches=int(L.b200bo_launch_count() - l0))
+# the other BASELINE configs through the public call (host candidates in, argmin + 10 seeds out)
+def _synth(n, d):
+    r = np.random.RandomState(0)
+    X = r.uniform(size=(n, d))
+    return X, np.sin(X.sum(1)) + 0.1 * r.randn(n)
+
+
+for tag, n, d, m, kind in [("c2_n1024_d8_ei", 1024, 8, 1 << 20, "ei"), ("c4_n2048_d16_poi_2constraints", 2048, 16, 1 << 19, "poi"),
+                           ("c5_n8192_d32_ucb_shard", 8192, 32, 1 << 18, "ucb")]:
+    X, y = _synth(n, d)
+    gp = bo.B200GaussianProcessRegressor(kernel=Matern(nu=2.5, length_scale=0.7 if d < 32 else 1.0), alpha=1e-6,
+                                         normalize_y=True, optimizer=None).fit(X, y)
+    cm = None
+    if kind == "poi":
+        c = np.column_stack([np.cos(X.sum(1)), np.sin(2 * X.sum(1))])
+        cm = bo.ConstraintModel(None, np.array([-np.inf, -0.5]), np.array([0.6, 0.5]))
+        for mdl, l in zip(cm.model, (0.9, 0.5)):
+            mdl.set_params(kernel=Matern(nu=2.5, length_scale=l), optimizer=None)
+        cm.fit(X, c)
+        a = bo.ProbabilityOfImprovement(xi=0.01)
+        a.y_max = float(y[cm.allowed(c)].max())
+    elif kind == "ei":
+        a = bo.ExpectedImprovement(xi=0.01)
+        a.y_max = float(y.max())
+    else:
+        a = bo.UpperConfidenceBound(kappa=2.576)
+    f = a._get_acq(gp=gp, constraint=cm)
+    xt = np.random.RandomState(1).uniform(size=(m, d))
+    f.argmin_topk(xt[: m // 8], 10)
+    t0 = time.perf_counter()
+    f.argmin_topk(xt, 10)
+    dt = time.perf_counter() - t0
+    out[tag] = dict(candidates=m, seconds=dt, cand_per_s=m / dt, n_gps=1 if cm is None else 3)
+
 # BASELINE configs[0]: README 2-D function, N=25, UCB - complete suggest() incl. the 6-start fit
 def black_box(x, y):
     return -(x**2) - (y - 1) ** 2 + 1
