@@ -144,6 +144,8 @@ extern "C" int b200bo_gp_create(b200bo_gp** out, int device) {
                             kPredictSmemBytesTc));
     CU(cudaFuncSetAttribute(predict_acq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             kPredictSmemBytesTc));
+    CU(cudaFuncSetAttribute(predict_acq_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            kPredictSmemBytesTc2));
     *out = gp;
     return B200BO_OK;
 }
@@ -758,10 +760,18 @@ extern "C" int b200bo_acq_eval_dev(const b200bo_acq* spec, const double* d_Xc, i
                 P.gp[g].linv_tc = spec->gps[g]->tc_linv.as<uint8_t>();
             }
             CU(cudaEventRecord(g0->ev0, stream));  // exclude the one-off tiling from the kernel time
-            if (dreg)
+            const char* tv = getenv("B200BO_TC_VARIANT");  // "1": non-overlapped version (A/B measurements)
+            if (dreg && !(tv && tv[0] == '1')) {
+                // overlapped version: two K* image buffers per CTA
+                P.scratch_stride *= 2;
+                if ((rc = g0->pscratch.reserve(sizeof(double) * (size_t)P.scratch_stride * g0->sm_count))) return rc;
+                P.scratch = g0->pscratch.as<double>();
+                predict_acq_tc2_kernel<<<grid, TC2_NT, kPredictSmemBytesTc2, stream>>>(P);
+            } else if (dreg) {
                 predict_acq_tc_kernel<true><<<grid, PNT, kPredictSmemBytesTc, stream>>>(P);
-            else
+            } else {
                 predict_acq_tc_kernel<false><<<grid, PNT, kPredictSmemBytesTc, stream>>>(P);
+            }
         } else if (predict_impl(g0->precision) == PREDICT_IMPL_DMMA) {
             if (dreg)
                 predict_acq_kernel<PREDICT_IMPL_DMMA, true><<<grid, PNT, kPredictSmemBytesDmma, stream>>>(P);

@@ -665,6 +665,325 @@ __global__ void __launch_bounds__(PNT, 1) predict_acq_tc_kernel(const PredictPar
     if (warp == 1) tc::tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------
+// fp32 mode, overlapped version (d <= 16): the K* build of the NEXT job runs on four dedicated
+// builder warps while the tensor cores work on the current one, so the fp64 front end disappears
+// behind the GEMM.  512 threads = 4 warp groups:
+//   warps 0-3   producer (warp 0, one lane), tcgen05.mma issuer (warp 1, one lane), 2 spare
+//   warps 4-7   epilogue: tcgen05.ld of their TMEM quadrant, warp transpose-reduce of v^2 over the
+//               32 rows, cross-warp sum, per-candidate acquisition epilogue
+//   warps 8-15  builders: two threads per candidate; K* in fp64 -> tf32 (hi,lo) operand images in a
+//               double-buffered global scratch, K* alpha_ in fp64
+// A job is one (candidate tile, GP).  mbarriers: full/empty (smem stages), accfull/accempty (TMEM
+// buffers), b_ready[2] (builders -> producer/epilogue), job_done[2] (epilogue -> builders).
+// ---------------------------------------------------------------------------------------
+constexpr int TC2_NT = 512;       // 16 warps: 4 (producer, MMA, 2 spare) + 4 epilogue + 8 builders
+constexpr int TC2_NB = 256;       // builder threads: two per candidate column (row halves of every chunk)
+constexpr int kPredictSmemBytesTc2 = TC_STAGES * TC_STAGE_BYTES + 2 * PA_CHUNK * kPredictMaxDimRegs * 8;  // 212992
+
+template <int COV>
+__device__ __forceinline__ void tc2_build_job(const PredictParams& P, const GpDev& G, long long c0, int btid,
+                                              uint8_t* __restrict__ Bimg, double* xs_s, double* mu_out) {
+    const int d = P.d, np = G.np;
+    const int c = btid & (PBN - 1), half = btid >> 7;
+    double xc[kPredictMaxDimRegs];
+    {
+        const long long gi = c0 + c;
+#pragma unroll
+        for (int j = 0; j < kPredictMaxDimRegs; ++j) {
+            double v = 0.0;
+            if (j < d && gi < P.m) {
+                v = P.Xc[gi * d + j];
+                if (G.xform && G.xform[j] == B200BO_XFORM_ROUND) v = rint(v);
+                v = v / G.ls[j];
+            }
+            xc[j] = v;
+        }
+    }
+    const int chunk_pieces = PA_CHUNK * d / 2;
+    auto load_chunk = [&](int buf, int ch) {
+        const double* src = G.Xs + (size_t)ch * PA_CHUNK * d;
+        double* dst = xs_s + (size_t)buf * PA_CHUNK * kPredictMaxDimRegs;
+        for (int q = btid; q < chunk_pieces; q += TC2_NB) cp_async16_cg(dst + 2 * q, src + 2 * q);
+    };
+    const int nch = np / PA_CHUNK;
+    load_chunk(0, 0);
+    cp_async_commit();
+    double mu_acc = 0.0;
+    constexpr int R = 8;
+    for (int ch = 0; ch < nch; ++ch) {
+        if (ch + 1 < nch) load_chunk((ch + 1) & 1, ch + 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        tc::named_bar_sync(2, TC2_NB);
+        const double* xs = xs_s + (size_t)(ch & 1) * PA_CHUNK * kPredictMaxDimRegs;
+        for (int r0 = half * (PA_CHUNK / 2); r0 < (half + 1) * (PA_CHUNK / 2); r0 += R) {
+            double r2[R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) r2[q] = 0.0;
+            if ((d & 1) == 0) {
+#pragma unroll
+                for (int j = 0; j < kPredictMaxDimRegs; j += 2) {
+                    if (j < d) {
+#pragma unroll
+                        for (int q = 0; q < R; ++q) {
+                            const double2 xv = *reinterpret_cast<const double2*>(xs + (r0 + q) * d + j);
+                            const double d0 = xc[j] - xv.x, d1 = xc[j + 1] - xv.y;
+                            r2[q] = fma(d0, d0, r2[q]);
+                            r2[q] = fma(d1, d1, r2[q]);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kPredictMaxDimRegs; ++j) {
+                    if (j < d) {
+#pragma unroll
+                        for (int q = 0; q < R; ++q) {
+                            const double df = xc[j] - xs[(r0 + q) * d + j];
+                            r2[q] = fma(df, df, r2[q]);
+                        }
+                    }
+                }
+            }
+            float hi[R], lo[R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int n = ch * PA_CHUNK + r0 + q;
+                double kv = G.constv * cov_eval<COV>(r2[q]);
+                if (n >= G.n) kv = 0.0;
+                hi[q] = tc::to_tf32((float)kv);
+                lo[q] = tc::to_tf32((float)(kv - (double)hi[q]));
+                mu_acc = fma(__ldg(G.alphav + n), kv, mu_acc);
+            }
+            const int n0 = ch * PA_CHUNK + r0;
+            uint8_t* img = Bimg + (size_t)(n0 >> 5) * (2 * tc::kTcImgBytes);
+#pragma unroll
+            for (int h4 = 0; h4 < 2; ++h4) {
+                const int off = tc::tc_img_offset(c, (n0 & 31) + 4 * h4);
+                *reinterpret_cast<float4*>(img + off) =
+                    make_float4(hi[4 * h4], hi[4 * h4 + 1], hi[4 * h4 + 2], hi[4 * h4 + 3]);
+                *reinterpret_cast<float4*>(img + tc::kTcImgBytes + off) =
+                    make_float4(lo[4 * h4], lo[4 * h4 + 1], lo[4 * h4 + 2], lo[4 * h4 + 3]);
+            }
+        }
+        tc::named_bar_sync(2, TC2_NB);
+    }
+    cp_async_wait<0>();
+    *mu_out = mu_acc;
+}
+
+// Row blocks are processed in PAIRS against each K* stage (two TMEM accumulators per buffer), which
+// halves the HBM traffic of the K* images - the binding resource of this kernel (their 0.6 GB
+// working set cannot live in L2).  Stage = [A(ib0) hi|lo][A(ib1) hi|lo][B hi|lo] = 96 KiB, 2 stages.
+constexpr int TC2_STAGES = 2;
+constexpr int TC2_STAGE_BYTES = 6 * tc::kTcImgBytes;  // 98304
+constexpr int TC2_TMEM_COLS = 512;                    // 2 buffers x 2 row blocks x 128 columns
+static_assert(TC2_STAGES * TC2_STAGE_BYTES + 2 * PA_CHUNK * kPredictMaxDimRegs * 8 == kPredictSmemBytesTc2, "smem");
+
+__global__ void __launch_bounds__(TC2_NT, 1) predict_acq_tc2_kernel(const PredictParams P) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double mu_s[2][2][PBN];  // [job parity][row half][candidate]
+    __shared__ float red_s[4][PBN];
+    __shared__ uint64_t full_bar[TC2_STAGES], empty_bar[TC2_STAGES], accfull_bar[2], accempty_bar[2];
+    __shared__ uint64_t bready_bar[2], jobdone_bar[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t* stage_mem = reinterpret_cast<uint8_t*>(smem);
+    double* xs_s = reinterpret_cast<double*>(stage_mem + TC2_STAGES * TC2_STAGE_BYTES);
+    uint8_t* scratch = reinterpret_cast<uint8_t*>(P.scratch + (long long)blockIdx.x * P.scratch_stride);
+    const size_t buf_bytes = (size_t)P.scratch_stride * 4;  // two buffers of scratch_stride*4 bytes each
+    const long long ntiles = (P.m + PBN - 1) / PBN;
+    const long long my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const long long njobs = my_tiles * P.n_gps;
+    constexpr int KT_PER_BLOCK = PBM / tc::kTcK;  // 4 k-tiles per 128 rows
+    constexpr uint32_t IMG2 = 2 * tc::kTcImgBytes;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC2_STAGES; ++s) {
+            tc::mbar_init(&full_bar[s], 1);
+            tc::mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            tc::mbar_init(&accfull_bar[b], 1);
+            tc::mbar_init(&accempty_bar[b], 4);
+            tc::mbar_init(&bready_bar[b], TC2_NB / 32);
+            tc::mbar_init(&jobdone_bar[b], 4);
+        }
+        tc::mbar_fence_init();
+    }
+    if (warp == 1) tc::tmem_alloc(&tmem_base_s, TC2_TMEM_COLS);
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ------------------------------ producer -------------------------------------------
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long long j = 0; j < njobs; ++j) {
+                const GpDev& G = P.gp[j % P.n_gps];
+                const int nb = G.np / PBM, nkt_row = G.np / tc::kTcK;
+                const uint8_t* Bimg = scratch + (size_t)(j & 1) * buf_bytes;
+                tc::mbar_wait(&bready_bar[j & 1], (uint32_t)((j >> 1) & 1));
+                for (int ib0 = 0; ib0 < nb; ib0 += 2) {
+                    const bool two = ib0 + 1 < nb;
+                    const int nkt0 = (ib0 + 1) * KT_PER_BLOCK, nkt = two ? nkt0 + KT_PER_BLOCK : nkt0;
+                    const uint8_t* A0 = G.linv_tc + (size_t)ib0 * nkt_row * IMG2;
+                    const uint8_t* A1 = A0 + (size_t)nkt_row * IMG2;
+                    for (int kt = 0; kt < nkt; ++kt, ++it) {
+                        const int s = it % TC2_STAGES;
+                        tc::mbar_wait(&empty_bar[s], ((it / TC2_STAGES) & 1) ^ 1);
+                        const bool a0 = kt < nkt0;
+                        tc::mbar_arrive_expect_tx(&full_bar[s], (1u + (a0 ? 1u : 0u) + (two ? 1u : 0u)) * IMG2);
+                        uint8_t* dst = stage_mem + (size_t)s * TC2_STAGE_BYTES;
+                        if (a0) tc::bulk_g2s(dst, A0 + (size_t)kt * IMG2, IMG2, &full_bar[s]);
+                        if (two) tc::bulk_g2s(dst + IMG2, A1 + (size_t)kt * IMG2, IMG2, &full_bar[s]);
+                        tc::bulk_g2s(dst + 2 * IMG2, Bimg + (size_t)kt * IMG2, IMG2, &full_bar[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------ tcgen05.mma issuer ---------------------------------
+        if (lane == 0) {
+            const uint32_t idesc = tc::umma_idesc_tf32(128, 128);
+            uint32_t it = 0, ai = 0;
+            for (long long j = 0; j < njobs; ++j) {
+                const GpDev& G = P.gp[j % P.n_gps];
+                const int nb = G.np / PBM;
+                for (int ib0 = 0; ib0 < nb; ib0 += 2, ++ai) {
+                    const bool two = ib0 + 1 < nb;
+                    const int nkt0 = (ib0 + 1) * KT_PER_BLOCK, nkt = two ? nkt0 + KT_PER_BLOCK : nkt0;
+                    const uint32_t buf = ai & 1;
+                    tc::mbar_wait(&accempty_bar[buf], ((ai >> 1) & 1) ^ 1);
+                    tc::tc_fence_after_sync();
+                    const uint32_t d0 = tmem_base + buf * 256, d1 = d0 + 128;
+                    for (int kt = 0; kt < nkt; ++kt, ++it) {
+                        const int s = it % TC2_STAGES;
+                        tc::mbar_wait(&full_bar[s], (it / TC2_STAGES) & 1);
+                        tc::tc_fence_after_sync();
+                        const uint32_t base = tc::smem_u32(stage_mem + (size_t)s * TC2_STAGE_BYTES);
+                        const bool a0 = kt < nkt0;
+#pragma unroll
+                        for (int k8 = 0; k8 < tc::kTcK / 8; ++k8) {
+                            const uint32_t koff = k8 * 2 * tc::kTcLBO;
+                            const uint64_t b_hi = tc::umma_desc_kmajor_noswz(base + 2 * IMG2 + koff, tc::kTcLBO, tc::kTcSBO);
+                            const uint64_t b_lo =
+                                tc::umma_desc_kmajor_noswz(base + 2 * IMG2 + tc::kTcImgBytes + koff, tc::kTcLBO, tc::kTcSBO);
+                            if (a0) {
+                                const uint64_t a_hi = tc::umma_desc_kmajor_noswz(base + koff, tc::kTcLBO, tc::kTcSBO);
+                                const uint64_t a_lo =
+                                    tc::umma_desc_kmajor_noswz(base + tc::kTcImgBytes + koff, tc::kTcLBO, tc::kTcSBO);
+                                tc::umma_tf32(d0, a_hi, b_hi, idesc, (kt | k8) ? 1u : 0u);
+                                tc::umma_tf32(d0, a_hi, b_lo, idesc, 1u);
+                                tc::umma_tf32(d0, a_lo, b_hi, idesc, 1u);
+                            }
+                            if (two) {
+                                const uint64_t a_hi = tc::umma_desc_kmajor_noswz(base + IMG2 + koff, tc::kTcLBO, tc::kTcSBO);
+                                const uint64_t a_lo =
+                                    tc::umma_desc_kmajor_noswz(base + IMG2 + tc::kTcImgBytes + koff, tc::kTcLBO, tc::kTcSBO);
+                                tc::umma_tf32(d1, a_hi, b_hi, idesc, (kt | k8) ? 1u : 0u);
+                                tc::umma_tf32(d1, a_hi, b_lo, idesc, 1u);
+                                tc::umma_tf32(d1, a_lo, b_hi, idesc, 1u);
+                            }
+                        }
+                        tc::umma_commit(&empty_bar[s]);
+                    }
+                    tc::umma_commit(&accfull_bar[buf]);
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ------------------------------ epilogue --------------------------------------------
+        const int q = warp & 3, etid = tid - 128;
+        uint32_t ai = 0;
+        double base_neg = 0.0, prod = 1.0;
+        for (long long j = 0; j < njobs; ++j) {
+            const int g = (int)(j % P.n_gps);
+            const GpDev& G = P.gp[g];
+            const long long tile = blockIdx.x + (j / P.n_gps) * gridDim.x;
+            const int nb = G.np / PBM;
+            float csum[4] = {0.f, 0.f, 0.f, 0.f};  // columns lane, lane+32, lane+64, lane+96
+            for (int ib0 = 0; ib0 < nb; ib0 += 2, ++ai) {
+                const bool two = ib0 + 1 < nb;
+                const uint32_t buf = ai & 1;
+                tc::mbar_wait(&accfull_bar[buf], (ai >> 1) & 1);
+                tc::tc_fence_after_sync();
+                const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
+                const int nchunk = two ? 8 : 4;
+                for (int cc = 0; cc < nchunk; ++cc) {
+                    uint32_t r[32];
+                    tc::tmem_ld_32x32(taddr + cc * 32, r);
+                    tc::tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float x = __uint_as_float(r[i]);
+                        v[i] = x * x;
+                    }
+                    // warp transpose-reduce: afterwards lane L holds the sum over the 32 rows of column L
+#pragma unroll
+                    for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+                        for (int i = 0; i < s; ++i) {
+                            const bool up = (lane & s) != 0;
+                            const float send = up ? v[i] : v[i + s];
+                            const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+                            v[i] = (up ? v[i + s] : v[i]) + recv;
+                        }
+                    }
+                    const int c4 = cc & 3;
+                    csum[0] += (c4 == 0) ? v[0] : 0.f;
+                    csum[1] += (c4 == 1) ? v[0] : 0.f;
+                    csum[2] += (c4 == 2) ? v[0] : 0.f;
+                    csum[3] += (c4 == 3) ? v[0] : 0.f;
+                }
+                tc::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&accempty_bar[buf]);
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) red_s[q][cc * 32 + lane] = csum[cc];
+            tc::named_bar_sync(1, 128);
+            const double colsq =
+                (((double)red_s[0][etid] + (double)red_s[1][etid]) + (double)red_s[2][etid]) + (double)red_s[3][etid];
+            tc::mbar_wait(&bready_bar[j & 1], (uint32_t)((j >> 1) & 1));  // acquire the builders' mean
+            candidate_epilogue(P, G, g, mu_s[j & 1][0][etid] + mu_s[j & 1][1][etid], colsq, tile * PBN + etid,
+                               base_neg, prod);
+            tc::named_bar_sync(1, 128);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&jobdone_bar[j & 1]);
+        }
+    } else if (warp >= 8) {
+        // ------------------------------ builders ---------------------------------------------
+        const int btid = tid - 256;
+        for (long long j = 0; j < njobs; ++j) {
+            const int g = (int)(j % P.n_gps);
+            const GpDev& G = P.gp[g];
+            const long long tile = blockIdx.x + (j / P.n_gps) * gridDim.x;
+            tc::mbar_wait(&jobdone_bar[j & 1], (uint32_t)(((j >> 1) & 1) ^ 1));  // buffer j&1 free again
+            uint8_t* Bimg = scratch + (size_t)(j & 1) * buf_bytes;
+            double mu = 0.0;
+            switch (cov_code(G.family, G.nu)) {
+                case 0: tc2_build_job<0>(P, G, tile * PBN, btid, Bimg, xs_s, &mu); break;
+                case 1: tc2_build_job<1>(P, G, tile * PBN, btid, Bimg, xs_s, &mu); break;
+                case 2: tc2_build_job<2>(P, G, tile * PBN, btid, Bimg, xs_s, &mu); break;
+                default: tc2_build_job<3>(P, G, tile * PBN, btid, Bimg, xs_s, &mu); break;
+            }
+            mu_s[j & 1][btid >> 7][btid & (PBN - 1)] = mu;
+            tc::fence_proxy_async_global();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bready_bar[j & 1]);
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, TC2_TMEM_COLS);
+}
+
 // L^-1 (fp64, row-major) -> tf32 (hi, lo) operand images [ib][kt][hi|lo][16 KiB] (lower k-tiles only)
 __global__ void __launch_bounds__(256) pretile_linv_tc_kernel(const double* __restrict__ W, int np,
                                                               uint8_t* __restrict__ out) {
