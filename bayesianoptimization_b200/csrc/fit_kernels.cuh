@@ -55,7 +55,9 @@ __global__ void kbuild_kernel(const double* __restrict__ Xs, double* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------
-// Generic fp64 GEMM on 64x64 tiles (fit-side building block):
+// Generic fp64 GEMM on 64x64 tiles (fit-side building block; inner product on the fp64 tensor
+// path, mma.sync m8n8k4 - the trailing SYRK/GEMM updates of the blocked Cholesky, the triangular
+// inverse recursion and K^-1 all run through it):
 //   C[m][n] = beta*C[m][n] + alpha * sum_k opA(m,k) * opB(k,n)
 //   opA(m,k) = TA ? A[k*lda+m] : A[m*lda+k];  opB(k,n) = TB ? B[n*ldb+k] : B[k*ldb+n]
 // M, N multiples of 64; K multiple of 16.  lower_only: skip tiles strictly above the diagonal.
@@ -75,15 +77,18 @@ dgemm64_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, 
     A += (long long)blockIdx.z * sA;
     B += (long long)blockIdx.z * sB;
     C += (long long)blockIdx.z * sC;
-    __shared__ double As[16][66];
-    __shared__ double Bs[16][66];
-    const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
-    double acc[4][4];
+    // k-major tiles, row stride 68 doubles = 8 words (mod 32): the 4 k-rows x 4 columns an LDS.64
+    // half-warp touches for an m8n8k4 fragment fall on disjoint banks
+    __shared__ double As[16][68];
+    __shared__ double Bs[16][68];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2;  // warp tile: rows wm*16..+16, cols wn*32..+32
+    const int g = lane >> 2, t4 = lane & 3;
+    double acc[2][4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     int kbeg = 0, kend = K;
     if (kmode == 1) kend = min(K, m0 + 64);
@@ -110,28 +115,35 @@ dgemm64_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, 
             }
         }
         __syncthreads();
+        // fp64 tensor path: mma.sync m8n8k4 (DMMA); 2 x 4 fragments per warp and k-step
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            double a[4], b[4];
+        for (int k4 = 0; k4 < 4; ++k4) {
+            double a[2], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty + 16 * i];
+            for (int i = 0; i < 2; ++i) a[i] = As[k4 * 4 + t4][wm * 16 + i * 8 + g];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k4 * 4 + t4][wn * 32 + j * 8 + g];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                                 : "d"(a[i]), "d"(b[j]));
         }
         __syncthreads();
     }
+    // C fragment: row = g, columns 2*t4 + {0,1}
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            double* c = C + (size_t)(m0 + ty + 16 * i) * ldc + n0 + tx + 16 * j;
-            const double v = alpha * acc[i][j];
-            *c = (beta == 0.0) ? v : fma(beta, *c, v);
-        }
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double* c = C + (size_t)(m0 + wm * 16 + i * 8 + g) * ldc + n0 + wn * 32 + j * 8 + 2 * t4 + e;
+                const double v = alpha * acc[i][j][e];
+                *c = (beta == 0.0) ? v : fma(beta, *c, v);
+            }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 D, N_TRAIN, LS, ALPHA, XI, KSEEDS = 16, 4096, 0.7, 1e-6, 0.01, 10
 M_PER_GPU = 1 << 20
 N_CAND_BUFFERS = 3  # rotated so that no step re-reads candidates from L2
-NCU_DRAM_BYTES_PER_LAUNCH = 568.12e9 + 34.40e9  # from the committed ncu capture (see traffic_source)
+NCU_DRAM_BYTES_PER_LAUNCH = 569.44e9 + 34.40e9  # from the committed ncu capture (see traffic_source)
 
 
 def flops_per_candidate(n, d, n_gps=1):
@@ -385,10 +385,12 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
-                "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "bound": "tensor", "pipe": "fp64 tensor path: mma.sync m8n8k4 f64 (SASS DMMA; ncu "
+                "sm__pipe_tensor_subpipe_dmma) - tcgen05.mma has no f64 kind",
+                "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": ach_tf / fp64_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload, ncu "
-                                  "--set full capture profiles/r01_v4_predict_acq_dmma_ncu_summary.txt (K* scratch "
+                                  "--set full capture profiles/r01_v6_predict_acq_dmma_ncu_summary.txt (K* scratch "
                                   "streams through HBM: 0.6 GB working set > L2)",
                 "kernel": "predict_acq_kernel", "kernel_ms": k_ms,
                 "peak_source": peak_src,
