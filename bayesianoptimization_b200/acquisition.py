@@ -78,6 +78,8 @@ class FusedAcquisition:
         self.spec = spec
 
     def _candidates(self, x):
+        for g in self._keep:  # an LML evaluation in between re-uses the factor buffers: refit lazily
+            g._ensure_device_fit()
         x = B.c_f64(np.asarray(x, dtype=np.float64).reshape(-1, self.dim))
         if not np.isfinite(x).all():  # sklearn's predict raises the same way (validate_data)
             raise ValueError("Input X contains NaN or infinity.")

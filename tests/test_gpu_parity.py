@@ -509,6 +509,18 @@ def test_unsupported_kernel_raises(bo):
         gp.fit(np.random.rand(5, 2), np.random.rand(5))
 
 
+def test_closure_survives_lml_evaluation(bo, golden):
+    """log_marginal_likelihood(theta) re-uses the device factor buffers; a closure created before must
+    transparently see the fitted model again."""
+    g = golden("c2s_ei")
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=0.7)).fit(g["X"], g["y"])
+    f = bo.UpperConfidenceBound(kappa=float(g["kappa"]))._get_acq(gp=gp)
+    y0 = f(g["xt"][:300])
+    gp.log_marginal_likelihood(np.log([0.3]), eval_gradient=True)
+    assert np.array_equal(f(g["xt"][:300]), y0)
+    assert_allclose(y0, g["acq_ucb"][:300], rtol=RTOL, atol=1e-12)
+
+
 def test_prior_predict_unfitted(bo):
     gp = make_gp(bo, Matern(nu=2.5))
     mu, sd = gp.predict(np.random.rand(7, 3), return_std=True)
