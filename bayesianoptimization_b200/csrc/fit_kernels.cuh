@@ -179,10 +179,11 @@ potrf_diag_kernel(double* A, int ld, int j0, double* Dinv, int ldd, int* info) {
             S[tid][k] = S[tid][k] / lkk;
         }
         __syncthreads();
-        const int rem = 63 - k;  // trailing block (k+1..63)^2, lower part: S[i][j] -= S[i][k]*S[j][k]
-        for (int idx = tid; idx < rem * rem; idx += 256) {
-            const int i = k + 1 + idx / rem, j = k + 1 + idx % rem;
-            if (j <= i) S[i][j] = fma(-S[i][k], S[j][k], S[i][j]);
+        // trailing block (k+1..63)^2, lower part: S[i][j] -= S[i][k]*S[j][k]; 16x16 thread grid,
+        // no integer divisions on the critical path
+        for (int i = k + 1 + (tid >> 4); i < 64; i += 16) {
+            const double lik = S[i][k];
+            for (int j = k + 1 + (tid & 15); j <= i; j += 16) S[i][j] = fma(-lik, S[j][k], S[i][j]);
         }
         __syncthreads();
     }

@@ -866,3 +866,20 @@ def test_sharded_argmin_topk_single_process_group(bo, golden):
         vals[r, 1:1 + len(t)], idxs[r, 1:1 + len(t)] = f(g["xt"][s0:s1][t]), s0 + t
     bi, bv, top = merge_selection(vals, idxs, 10)
     assert bi == int(g["argmin"]) and list(top) == list(g["top10"])
+
+
+def test_empty_and_single_candidate_batches(bo, golden):
+    """Edge shapes: zero candidates (empty result), one candidate, (d,) vs (1,d) input, argmin on 1."""
+    g = golden("c2s_ei")
+    gp = make_gp(bo, Matern(nu=2.5, length_scale=0.7)).fit(g["X"], g["y"])
+    f = bo.UpperConfidenceBound(kappa=2.0)._get_acq(gp=gp)
+    assert f(np.empty((0, 8))).shape == (0,)
+    y1 = f(g["xt"][3])
+    y2 = f(g["xt"][3:4])
+    assert y1.shape == (1,) and np.array_equal(y1, y2)
+    idx, val, top = f.argmin_topk(g["xt"][3:4], 10)
+    assert idx == 0 and val == y1[0] and list(top) == [0]
+    with pytest.raises(ValueError):
+        f(np.array([[np.nan] * 8]))
+    with pytest.raises(ValueError):
+        gp.predict(np.zeros((3, 5)))
