@@ -764,6 +764,7 @@ extern "C" int b200bo_acq_eval_dev(const b200bo_acq* spec, const double* d_Xc, i
             if (dreg && !(tv && tv[0] == '1')) {
                 // overlapped version: two K* image buffers per CTA
                 P.scratch_stride *= 2;
+                if (const char* dbg = getenv("B200BO_TC_DEBUG")) P.pad0 = atoi(dbg);
                 if ((rc = g0->pscratch.reserve(sizeof(double) * (size_t)P.scratch_stride * g0->sm_count))) return rc;
                 P.scratch = g0->pscratch.as<double>();
                 predict_acq_tc2_kernel<<<grid, TC2_NT, kPredictSmemBytesTc2, stream>>>(P);

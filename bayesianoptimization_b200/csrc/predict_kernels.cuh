@@ -774,10 +774,12 @@ __device__ __forceinline__ void tc2_build_job(const PredictParams& P, const GpDe
 }
 
 // Row blocks are processed in PAIRS against each K* stage (two TMEM accumulators per buffer), which
-// halves the HBM traffic of the K* images - the binding resource of this kernel (their 0.6 GB
-// working set cannot live in L2).  Stage = [A(ib0) hi|lo][A(ib1) hi|lo][B hi|lo] = 96 KiB, 2 stages.
-constexpr int TC2_STAGES = 2;
-constexpr int TC2_STAGE_BYTES = 6 * tc::kTcImgBytes;  // 98304
+// halves the HBM traffic of the K* images (their 0.6 GB working set cannot live in L2).  A stage
+// holds HALF a k-tile (16 k) of every operand image: [A(ib0) hi|lo][A(ib1) hi|lo][B hi|lo], 6 x 8 KiB;
+// four stages keep three loads in flight behind the MMAs (the 2-stage/32-k version was latency bound).
+constexpr int TC2_STAGES = 4;
+constexpr int TC2_HALF = tc::kTcImgBytes / 2;         // 8192: k 0..15 or 16..31 of an image
+constexpr int TC2_STAGE_BYTES = 6 * TC2_HALF;         // 49152
 constexpr int TC2_TMEM_COLS = 512;                    // 2 buffers x 2 row blocks x 128 columns
 static_assert(TC2_STAGES * TC2_STAGE_BYTES + 2 * PA_CHUNK * kPredictMaxDimRegs * 8 == kPredictSmemBytesTc2, "smem");
 
@@ -819,9 +821,11 @@ __global__ void __launch_bounds__(TC2_NT, 1) predict_acq_tc2_kernel(const Predic
     tc::tc_fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
 
+    // measurement hooks (B200BO_TC_DEBUG): bit 0 = builders only, bit 1 = GEMM only (results invalid)
+    const bool dbg_no_gemm = (P.pad0 & 1) != 0, dbg_no_build = (P.pad0 & 2) != 0;
     if (warp == 0) {
         // ------------------------------ producer -------------------------------------------
-        if (lane == 0) {
+        if (lane == 0 && !dbg_no_gemm) {
             uint32_t it = 0;
             for (long long j = 0; j < njobs; ++j) {
                 const GpDev& G = P.gp[j % P.n_gps];
@@ -833,22 +837,34 @@ __global__ void __launch_bounds__(TC2_NT, 1) predict_acq_tc2_kernel(const Predic
                     const int nkt0 = (ib0 + 1) * KT_PER_BLOCK, nkt = two ? nkt0 + KT_PER_BLOCK : nkt0;
                     const uint8_t* A0 = G.linv_tc + (size_t)ib0 * nkt_row * IMG2;
                     const uint8_t* A1 = A0 + (size_t)nkt_row * IMG2;
-                    for (int kt = 0; kt < nkt; ++kt, ++it) {
+                    for (int ht = 0; ht < 2 * nkt; ++ht, ++it) {
+                        const int kt = ht >> 1;
+                        const size_t hoff = (size_t)(ht & 1) * TC2_HALF;  // which 16-k half of the images
                         const int s = it % TC2_STAGES;
                         tc::mbar_wait(&empty_bar[s], ((it / TC2_STAGES) & 1) ^ 1);
                         const bool a0 = kt < nkt0;
-                        tc::mbar_arrive_expect_tx(&full_bar[s], (1u + (a0 ? 1u : 0u) + (two ? 1u : 0u)) * IMG2);
+                        tc::mbar_arrive_expect_tx(&full_bar[s], (1u + (a0 ? 1u : 0u) + (two ? 1u : 0u)) * 2u * TC2_HALF);
                         uint8_t* dst = stage_mem + (size_t)s * TC2_STAGE_BYTES;
-                        if (a0) tc::bulk_g2s(dst, A0 + (size_t)kt * IMG2, IMG2, &full_bar[s]);
-                        if (two) tc::bulk_g2s(dst + IMG2, A1 + (size_t)kt * IMG2, IMG2, &full_bar[s]);
-                        tc::bulk_g2s(dst + 2 * IMG2, Bimg + (size_t)kt * IMG2, IMG2, &full_bar[s]);
+                        const uint8_t* a0p = A0 + (size_t)kt * IMG2 + hoff;
+                        const uint8_t* a1p = A1 + (size_t)kt * IMG2 + hoff;
+                        const uint8_t* bp = Bimg + (size_t)kt * IMG2 + hoff;
+                        if (a0) {
+                            tc::bulk_g2s(dst, a0p, TC2_HALF, &full_bar[s]);
+                            tc::bulk_g2s(dst + TC2_HALF, a0p + tc::kTcImgBytes, TC2_HALF, &full_bar[s]);
+                        }
+                        if (two) {
+                            tc::bulk_g2s(dst + 2 * TC2_HALF, a1p, TC2_HALF, &full_bar[s]);
+                            tc::bulk_g2s(dst + 3 * TC2_HALF, a1p + tc::kTcImgBytes, TC2_HALF, &full_bar[s]);
+                        }
+                        tc::bulk_g2s(dst + 4 * TC2_HALF, bp, TC2_HALF, &full_bar[s]);
+                        tc::bulk_g2s(dst + 5 * TC2_HALF, bp + tc::kTcImgBytes, TC2_HALF, &full_bar[s]);
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------ tcgen05.mma issuer ---------------------------------
-        if (lane == 0) {
+        if (lane == 0 && !dbg_no_gemm) {
             const uint32_t idesc = tc::umma_idesc_tf32(128, 128);
             uint32_t it = 0, ai = 0;
             for (long long j = 0; j < njobs; ++j) {
@@ -861,31 +877,29 @@ __global__ void __launch_bounds__(TC2_NT, 1) predict_acq_tc2_kernel(const Predic
                     tc::mbar_wait(&accempty_bar[buf], ((ai >> 1) & 1) ^ 1);
                     tc::tc_fence_after_sync();
                     const uint32_t d0 = tmem_base + buf * 256, d1 = d0 + 128;
-                    for (int kt = 0; kt < nkt; ++kt, ++it) {
+                    for (int ht = 0; ht < 2 * nkt; ++ht, ++it) {
+                        const int kt = ht >> 1;
                         const int s = it % TC2_STAGES;
                         tc::mbar_wait(&full_bar[s], (it / TC2_STAGES) & 1);
                         tc::tc_fence_after_sync();
                         const uint32_t base = tc::smem_u32(stage_mem + (size_t)s * TC2_STAGE_BYTES);
                         const bool a0 = kt < nkt0;
 #pragma unroll
-                        for (int k8 = 0; k8 < tc::kTcK / 8; ++k8) {
+                        for (int k8 = 0; k8 < 2; ++k8) {
                             const uint32_t koff = k8 * 2 * tc::kTcLBO;
-                            const uint64_t b_hi = tc::umma_desc_kmajor_noswz(base + 2 * IMG2 + koff, tc::kTcLBO, tc::kTcSBO);
-                            const uint64_t b_lo =
-                                tc::umma_desc_kmajor_noswz(base + 2 * IMG2 + tc::kTcImgBytes + koff, tc::kTcLBO, tc::kTcSBO);
+                            const uint64_t b_hi = tc::umma_desc_kmajor_noswz(base + 4 * TC2_HALF + koff, tc::kTcLBO, tc::kTcSBO);
+                            const uint64_t b_lo = tc::umma_desc_kmajor_noswz(base + 5 * TC2_HALF + koff, tc::kTcLBO, tc::kTcSBO);
                             if (a0) {
                                 const uint64_t a_hi = tc::umma_desc_kmajor_noswz(base + koff, tc::kTcLBO, tc::kTcSBO);
-                                const uint64_t a_lo =
-                                    tc::umma_desc_kmajor_noswz(base + tc::kTcImgBytes + koff, tc::kTcLBO, tc::kTcSBO);
-                                tc::umma_tf32(d0, a_hi, b_hi, idesc, (kt | k8) ? 1u : 0u);
+                                const uint64_t a_lo = tc::umma_desc_kmajor_noswz(base + TC2_HALF + koff, tc::kTcLBO, tc::kTcSBO);
+                                tc::umma_tf32(d0, a_hi, b_hi, idesc, (ht | k8) ? 1u : 0u);
                                 tc::umma_tf32(d0, a_hi, b_lo, idesc, 1u);
                                 tc::umma_tf32(d0, a_lo, b_hi, idesc, 1u);
                             }
                             if (two) {
-                                const uint64_t a_hi = tc::umma_desc_kmajor_noswz(base + IMG2 + koff, tc::kTcLBO, tc::kTcSBO);
-                                const uint64_t a_lo =
-                                    tc::umma_desc_kmajor_noswz(base + IMG2 + tc::kTcImgBytes + koff, tc::kTcLBO, tc::kTcSBO);
-                                tc::umma_tf32(d1, a_hi, b_hi, idesc, (kt | k8) ? 1u : 0u);
+                                const uint64_t a_hi = tc::umma_desc_kmajor_noswz(base + 2 * TC2_HALF + koff, tc::kTcLBO, tc::kTcSBO);
+                                const uint64_t a_lo = tc::umma_desc_kmajor_noswz(base + 3 * TC2_HALF + koff, tc::kTcLBO, tc::kTcSBO);
+                                tc::umma_tf32(d1, a_hi, b_hi, idesc, (ht | k8) ? 1u : 0u);
                                 tc::umma_tf32(d1, a_hi, b_lo, idesc, 1u);
                                 tc::umma_tf32(d1, a_lo, b_hi, idesc, 1u);
                             }
@@ -907,7 +921,7 @@ __global__ void __launch_bounds__(TC2_NT, 1) predict_acq_tc2_kernel(const Predic
             const long long tile = blockIdx.x + (j / P.n_gps) * gridDim.x;
             const int nb = G.np / PBM;
             float csum[4] = {0.f, 0.f, 0.f, 0.f};  // columns lane, lane+32, lane+64, lane+96
-            for (int ib0 = 0; ib0 < nb; ib0 += 2, ++ai) {
+            for (int ib0 = 0; ib0 < nb && !dbg_no_gemm; ib0 += 2, ++ai) {
                 const bool two = ib0 + 1 < nb;
                 const uint32_t buf = ai & 1;
                 tc::mbar_wait(&accfull_bar[buf], (ai >> 1) & 1);
@@ -967,7 +981,7 @@ __global__ void __launch_bounds__(TC2_NT, 1) predict_acq_tc2_kernel(const Predic
             tc::mbar_wait(&jobdone_bar[j & 1], (uint32_t)(((j >> 1) & 1) ^ 1));  // buffer j&1 free again
             uint8_t* Bimg = scratch + (size_t)(j & 1) * buf_bytes;
             double mu = 0.0;
-            switch (cov_code(G.family, G.nu)) {
+            if (!dbg_no_build) switch (cov_code(G.family, G.nu)) {
                 case 0: tc2_build_job<0>(P, G, tile * PBN, btid, Bimg, xs_s, &mu); break;
                 case 1: tc2_build_job<1>(P, G, tile * PBN, btid, Bimg, xs_s, &mu); break;
                 case 2: tc2_build_job<2>(P, G, tile * PBN, btid, Bimg, xs_s, &mu); break;
