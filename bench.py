@@ -390,7 +390,7 @@ def main():
                 "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": ach_tf / fp64_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload, ncu "
-                                  "--set full capture profiles/r01_v6_predict_acq_dmma_ncu_summary.txt (K* scratch "
+                                  "--set full capture profiles/r01_final_predict_acq_dmma_ncu_summary.txt (K* scratch "
                                   "streams through HBM: 0.6 GB working set > L2)",
                 "kernel": "predict_acq_kernel", "kernel_ms": k_ms,
                 "peak_source": peak_src,
