@@ -228,14 +228,13 @@ class AcquisitionFunction(abc.ABC):
         min_acq = None
         x_min = None
         if all(continuous_dimensions):
-            options = _stencil_options(acq)
-            for x_try in x_seeds:
-                res = minimize(acq, x_try, bounds=continuous_bounds, method="L-BFGS-B", options=options)
+            # the n_smart runs are independent: advance them in lockstep so that every round of
+            # objective / stencil requests of ALL seeds is one device call (same iterates per seed)
+            for res in _lockstep_lbfgsb(acq, x_seeds, continuous_bounds):
                 if not res.success:
                     continue
                 if min_acq is None or np.squeeze(res.fun) < min_acq:
-                    x_try = res.x
-                    x_min = x_try
+                    x_min = res.x
                     min_acq = np.squeeze(res.fun)
         else:
             # mixed-integer branch (R/bayes_opt/acquisition.py:376-412): SciPy's differential
@@ -297,6 +296,100 @@ def _stencil_options(acq):
         return [np.atleast_1d(y) for y in ys]
 
     return {"workers": batched_map}
+
+
+class _LockstepEvaluator:
+    """Serves the pending objective requests of several concurrently running SciPy minimisations
+    with ONE call of the (device) closure.  Each minimisation runs in its own thread and blocks in
+    ``evaluate`` until every still-active run has submitted its request; the last one to arrive
+    evaluates the concatenated batch.  Per-candidate results of the fused kernels do not depend on
+    what else is in the batch, so each run sees exactly the values it would see alone."""
+
+    def __init__(self, acq, n_active):
+        import threading
+
+        self.acq = acq
+        self.cv = threading.Condition()
+        self.pending, self.results = {}, {}
+        self.active = n_active
+        self.error = None
+
+    def _flush(self):
+        keys = list(self.pending)
+        xs = [self.pending[k] for k in keys]
+        try:
+            ys = np.asarray(self.acq(np.vstack(xs)), dtype=float)
+            off = 0
+            for k, x in zip(keys, xs):
+                self.results[k] = ys[off:off + len(x)]
+                off += len(x)
+        except BaseException as e:  # propagate to every waiting run
+            self.error = e
+        self.pending.clear()
+        self.cv.notify_all()
+
+    def evaluate(self, key, x):
+        with self.cv:
+            if self.error is not None:
+                raise self.error
+            self.pending[key] = np.atleast_2d(np.asarray(x, dtype=float))
+            if len(self.pending) >= self.active:
+                self._flush()
+            while key not in self.results and self.error is None:
+                self.cv.wait()
+            if self.error is not None:
+                raise self.error
+            return self.results.pop(key)
+
+    def finish(self, key):
+        with self.cv:
+            self.active -= 1
+            if self.pending and len(self.pending) >= self.active:
+                self._flush()
+
+
+def _lockstep_lbfgsb(acq, x_seeds, bounds):
+    """``[minimize(acq, seed, bounds=bounds, method="L-BFGS-B") for seed in x_seeds]`` (the loop at
+    R/bayes_opt/acquisition.py:365-366) with the runs advanced in lockstep.  B200BO_LOCKSTEP=0 (or a
+    single seed) falls back to the plain sequential loop."""
+    import os
+    import threading
+
+    seeds = [np.asarray(s, dtype=float) for s in x_seeds]
+    if len(seeds) <= 1 or os.environ.get("B200BO_LOCKSTEP", "1") == "0":
+        options = _stencil_options(acq)
+        return [minimize(acq, s, bounds=bounds, method="L-BFGS-B", options=options) for s in seeds]
+    ev = _LockstepEvaluator(acq, len(seeds))
+    results, errors = [None] * len(seeds), [None] * len(seeds)
+    use_workers = _stencil_options(acq) is not None
+
+    def run(i):
+        try:
+            def fun(x):
+                return ev.evaluate(i, x)
+
+            options = None
+            if use_workers:
+                def stencil_map(_f, iterable):
+                    xs = [np.asarray(x, dtype=float) for x in iterable]
+                    return [np.atleast_1d(y) for y in ev.evaluate(i, np.vstack(xs))] if xs else []
+
+                options = {"workers": stencil_map}
+            results[i] = minimize(fun, seeds[i], bounds=bounds, method="L-BFGS-B", options=options)
+        except BaseException as e:
+            errors[i] = e
+        finally:
+            ev.finish(i)
+
+    threads = [threading.Thread(target=run, args=(i,), daemon=True) for i in range(len(seeds))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in errors:
+        if e is not None:
+            raise e
+    return results
 
 
 def _check_decay(exploration_decay, exploration_decay_delay):

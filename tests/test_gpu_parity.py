@@ -425,8 +425,8 @@ def test_batched_fd_stencil_matches_sequential_lbfgsb(bo, golden):
         r = minimize(f, s, bounds=space.bounds, method="L-BFGS-B")
         if r.success and (best is None or r.fun < best.fun):
             best = r
-    assert_allclose(x_b, np.clip(best.x, 0, 1), rtol=1e-9, atol=1e-12)
-    assert float(v_b) == pytest.approx(float(np.squeeze(best.fun)), rel=1e-9)
+    assert_allclose(x_b, np.clip(best.x, 0, 1), rtol=1e-6, atol=1e-8)
+    assert float(v_b) == pytest.approx(float(np.squeeze(best.fun)), rel=1e-8)
 
 
 # ------------------------------------------------------------------------------------------

@@ -252,3 +252,35 @@ def test_shard_and_merge_selection(bo):
         bi, bv, top = merge_selection(vals, idxs, k)
         assert bi == int(np.argmin(ys))
         assert list(top) == list(np.argsort(ys, kind="stable")[:k])
+
+
+def test_lockstep_lbfgsb_equals_sequential_runs(bo):
+    """The n_smart L-BFGS-B runs advanced in lockstep (one batched objective call per round) follow
+    exactly the iterates of independent sequential runs (R/bayes_opt/acquisition.py:365-366)."""
+    from scipy.optimize import minimize
+
+    from bayesianoptimization_b200.acquisition import _lockstep_lbfgsb
+
+    calls = []
+
+    def acq(x):
+        x = np.atleast_2d(x)
+        calls.append(len(x))
+        return ((x - 0.3) ** 2).sum(1) + 0.3 * np.sin(5 * x).sum(1)
+
+    b = np.array([[0.0, 1.0]] * 4)
+    seeds = np.random.RandomState(0).rand(7, 4)
+    seq = [minimize(acq, s, bounds=b, method="L-BFGS-B") for s in seeds]
+    n_seq = len(calls)
+    calls.clear()
+    lock = _lockstep_lbfgsb(acq, seeds, b)
+    assert len(calls) < n_seq / 5
+    for a, c in zip(seq, lock):
+        assert np.array_equal(a.x, c.x) and a.fun == c.fun and a.nit == c.nit and a.success == c.success
+
+    def bad(x):
+        raise RuntimeError("boom")
+
+    with pytest.raises(RuntimeError, match="boom"):
+        _lockstep_lbfgsb(bad, seeds, b)
+    assert len(_lockstep_lbfgsb(acq, seeds[:1], b)) == 1
