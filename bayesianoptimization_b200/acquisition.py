@@ -186,6 +186,7 @@ class AcquisitionFunction(abc.ABC):
                     return -1 * self.base_acq(mean, std) * constraint.predict(x)
             return -1 * self.base_acq(mean, std)
 
+        acq._b200_vectorized = True
         return acq
 
     def _acq_min(self, acq, space, random_state, n_random=10_000, n_smart=10):
@@ -230,7 +231,9 @@ class AcquisitionFunction(abc.ABC):
         if all(continuous_dimensions):
             # the n_smart runs are independent: advance them in lockstep so that every round of
             # objective / stencil requests of ALL seeds is one device call (same iterates per seed)
-            for res in _lockstep_lbfgsb(acq, x_seeds, continuous_bounds):
+            # (only for closures known to map (M,d) -> (M,); arbitrary user callables run one by one)
+            batched = isinstance(acq, FusedAcquisition) or getattr(acq, "_b200_vectorized", False)
+            for res in _lockstep_lbfgsb(acq, x_seeds, continuous_bounds, lockstep=batched):
                 if not res.success:
                     continue
                 if min_acq is None or np.squeeze(res.fun) < min_acq:
@@ -348,7 +351,7 @@ class _LockstepEvaluator:
                 self._flush()
 
 
-def _lockstep_lbfgsb(acq, x_seeds, bounds):
+def _lockstep_lbfgsb(acq, x_seeds, bounds, lockstep=True):
     """``[minimize(acq, seed, bounds=bounds, method="L-BFGS-B") for seed in x_seeds]`` (the loop at
     R/bayes_opt/acquisition.py:365-366) with the runs advanced in lockstep.  B200BO_LOCKSTEP=0 (or a
     single seed) falls back to the plain sequential loop."""
@@ -356,8 +359,8 @@ def _lockstep_lbfgsb(acq, x_seeds, bounds):
     import threading
 
     seeds = [np.asarray(s, dtype=float) for s in x_seeds]
-    if len(seeds) <= 1 or os.environ.get("B200BO_LOCKSTEP", "1") == "0":
-        options = _stencil_options(acq)
+    if len(seeds) <= 1 or not lockstep or os.environ.get("B200BO_LOCKSTEP", "1") == "0":
+        options = _stencil_options(acq) if lockstep else None
         return [minimize(acq, s, bounds=bounds, method="L-BFGS-B", options=options) for s in seeds]
     ev = _LockstepEvaluator(acq, len(seeds))
     results, errors = [None] * len(seeds), [None] * len(seeds)
