@@ -53,6 +53,7 @@ def accelerate_acquisition(acq):
         "_get_acq": A.AcquisitionFunction._get_acq,
         "_get_acq_generic": A.AcquisitionFunction._get_acq_generic,
         "_random_sample_minimize": A.AcquisitionFunction._random_sample_minimize,
+        "_smart_minimize": A.AcquisitionFunction._smart_minimize,  # same algorithm, batched device calls
         "_acq_params": getattr(hooks, "_acq_params", A.AcquisitionFunction._acq_params),
     }
     acq.__class__ = type("B200" + name, (type(acq),), ns)
