@@ -58,7 +58,7 @@ constexpr int PBM = 128, PBN = 128, PBK = 16, PSTAGES = 3, PNT = 256;
 // each half-warp on disjoint bank octets -> 2 wavefronts per request, the minimum for 256 bytes.
 constexpr int PSTR_DFMA = 128, PSTR_DMMA = 132;
 // phase A needs (128 + 2*64) * d doubles (d <= 64 -> 128 KiB); phase B (DFMA) 96 KiB
-constexpr int kPredictSmemBytesDfma = 131072;
+constexpr int kPredictSmemBytesDfma = 133120;  // + 1 KiB staged alpha_
 constexpr int PBK_DMMA = 32;  // k-tile of the DMMA variant (one CTA barrier per 32 k)
 constexpr int kPredictSmemBytesDmma = PSTAGES * PBK_DMMA * 2 * PSTR_DMMA * 8;  // 202752
 constexpr int kPredictMaxDimRegs = 16;  // candidates held in registers when d <= 16
@@ -130,6 +130,7 @@ __device__ __forceinline__ void predict_phase_a_impl(const PredictParams& P, con
     const int d = P.d, np = G.np;
     double* xc_s = smem;                       // [d][PBN]
     double* xs_s = smem + (size_t)d * PBN;     // [2][PA_CHUNK][d]
+    double* al_s = xs_s + (size_t)2 * PA_CHUNK * d;  // [2][PA_CHUNK] alpha_ of the staged rows
     for (int idx = tid; idx < PBN * d; idx += PNT) {
         const int c = idx / d, j = idx - c * d;
         const long long gi = c0 + c;
@@ -146,6 +147,8 @@ __device__ __forceinline__ void predict_phase_a_impl(const PredictParams& P, con
         const double* src = G.Xs + (size_t)ch * PA_CHUNK * d;
         double* dst = xs_s + (size_t)buf * PA_CHUNK * d;
         for (int q = tid; q < chunk_pieces; q += PNT) cp_async16_cg(dst + 2 * q, src + 2 * q);
+        if (tid < PA_CHUNK / 2)
+            cp_async16_cg(al_s + buf * PA_CHUNK + 2 * tid, G.alphav + (size_t)ch * PA_CHUNK + 2 * tid);
     };
     const int nch = np / PA_CHUNK;
     load_chunk(0, 0);
@@ -165,6 +168,7 @@ __device__ __forceinline__ void predict_phase_a_impl(const PredictParams& P, con
         cp_async_wait<1>();
         __syncthreads();
         const double* xs = xs_s + (size_t)(ch & 1) * PA_CHUNK * d;
+        const double* al = al_s + (ch & 1) * PA_CHUNK;
         for (int r0 = half * (PA_CHUNK / 2); r0 < (half + 1) * (PA_CHUNK / 2); r0 += R) {
             double r2[R];
 #pragma unroll
@@ -215,7 +219,7 @@ __device__ __forceinline__ void predict_phase_a_impl(const PredictParams& P, con
                 } else {
                     Ks[(size_t)n * PBN + c] = kv;
                 }
-                mu_acc = fma(__ldg(G.alphav + n), kv, mu_acc);
+                mu_acc = fma(al[r0 + q], kv, mu_acc);
             }
             if (TC) {
                 const int n0 = ch * PA_CHUNK + r0;  // multiple of 8: two groups of 4 consecutive k
