@@ -284,3 +284,21 @@ def test_lockstep_lbfgsb_equals_sequential_runs(bo):
     with pytest.raises(RuntimeError, match="boom"):
         _lockstep_lbfgsb(bad, seeds, b)
     assert len(_lockstep_lbfgsb(acq, seeds[:1], b)) == 1
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` runs without a GPU and prints ONE JSON line with the contract keys."""
+    import json
+    import subprocess
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert key in j, key
+    assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port"
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in j["config"]
