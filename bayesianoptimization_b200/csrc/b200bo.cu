@@ -111,6 +111,34 @@ extern "C" int b200bo_device_count(void) {
     return n;
 }
 
+// device properties, timing events and the opt-in shared-memory sizes of the big kernels
+static int init_handle(b200bo_gp* gp) {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, gp->device));
+    gp->sm_count = prop.multiProcessorCount;
+    CU(cudaEventCreate(&gp->ev0));
+    CU(cudaEventCreate(&gp->ev1));
+    CU(cudaFuncSetAttribute(predict_acq_kernel<PREDICT_IMPL_DFMA, false>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDfma));
+    CU(cudaFuncSetAttribute(predict_acq_kernel<PREDICT_IMPL_DFMA, true>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDfma));
+    CU(cudaFuncSetAttribute(predict_acq_kernel<PREDICT_IMPL_DMMA, false>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDmma));
+    CU(cudaFuncSetAttribute(predict_acq_kernel<PREDICT_IMPL_DMMA, true>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDmma));
+    CU(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            kPotrfSmemBytes));
+    CU(cudaFuncSetAttribute(potrf_diag_legacy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            kPotrfLegacySmemBytes));
+    CU(cudaFuncSetAttribute(predict_acq_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            kPredictSmemBytesTc));
+    CU(cudaFuncSetAttribute(predict_acq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            kPredictSmemBytesTc));
+    CU(cudaFuncSetAttribute(predict_acq_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            kPredictSmemBytesTc2));
+    return B200BO_OK;
+}
+
 extern "C" int b200bo_gp_create(b200bo_gp** out, int device) {
     if (!out) return set_err(B200BO_ERR_ARG, "out is NULL");
     int ndev = 0;
@@ -125,27 +153,11 @@ extern "C" int b200bo_gp_create(b200bo_gp** out, int device) {
     CU(cudaSetDevice(device));
     b200bo_gp* gp = new b200bo_gp();
     gp->device = device;
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    gp->sm_count = prop.multiProcessorCount;
-    CU(cudaEventCreate(&gp->ev0));
-    CU(cudaEventCreate(&gp->ev1));
-    CU(cudaFuncSetAttribute(predict_acq_kernel<PREDICT_IMPL_DFMA, false>,
-                            cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDfma));
-    CU(cudaFuncSetAttribute(predict_acq_kernel<PREDICT_IMPL_DFMA, true>,
-                            cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDfma));
-    CU(cudaFuncSetAttribute(predict_acq_kernel<PREDICT_IMPL_DMMA, false>,
-                            cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDmma));
-    CU(cudaFuncSetAttribute(predict_acq_kernel<PREDICT_IMPL_DMMA, true>,
-                            cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDmma));
-    CU(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            kPotrfSmemBytes));
-    CU(cudaFuncSetAttribute(predict_acq_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            kPredictSmemBytesTc));
-    CU(cudaFuncSetAttribute(predict_acq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            kPredictSmemBytesTc));
-    CU(cudaFuncSetAttribute(predict_acq_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            kPredictSmemBytesTc2));
+    const int rc = init_handle(gp);
+    if (rc != B200BO_OK) {
+        b200bo_gp_destroy(gp);
+        return rc;
+    }
     *out = gp;
     return B200BO_OK;
 }
@@ -297,7 +309,7 @@ static int factorize(b200bo_gp* gp, const b200bo_kernel* kern, double jitter, in
         LAUNCHED();
     }
     {
-        dim3 blk(32, 8), grd((np + 31) / 32, (np + 7) / 8);
+        dim3 blk(32, 8), grd(np / 32, np / 32);
         kbuild_kernel<<<grd, blk>>>(gp->Xs.as<double>(), gp->K.as<double>(), n, np, d, kern->family,
                                     kern->family == B200BO_KERNEL_RBF ? B200BO_NU_INF : kern->nu,
                                     kern->const_value, jitter);
@@ -311,9 +323,17 @@ static int factorize(b200bo_gp* gp, const b200bo_kernel* kern, double jitter, in
     CU(cudaMemsetAsync(W, 0, sizeof(double) * (size_t)np * np));
     CU(cudaMemsetAsync(gp->info.p, 0, sizeof(int)));
     int rc;
-    // right-looking blocked Cholesky, panel width 64
+    // right-looking blocked Cholesky, panel width 64.  B200BO_POTRF=legacy selects the first
+    // (unblocked) diagonal-block kernel for A/B measurements; the factor is bit-identical.
+    const char* pv = getenv("B200BO_POTRF");
+    const bool legacy_potrf = pv && (pv[0] == 'l' || pv[0] == 'L');
     for (int j0 = 0; j0 < np; j0 += 64) {
-        potrf_diag_kernel<<<1, 256, kPotrfSmemBytes>>>(L, np, j0, W + (size_t)j0 * np + j0, np, gp->info.as<int>());
+        if (legacy_potrf)
+            potrf_diag_legacy_kernel<<<1, 256, kPotrfLegacySmemBytes>>>(L, np, j0, W + (size_t)j0 * np + j0, np,
+                                                                        gp->info.as<int>());
+        else
+            potrf_diag_kernel<<<1, 256, kPotrfSmemBytes>>>(L, np, j0, W + (size_t)j0 * np + j0, np,
+                                                           gp->info.as<int>());
         LAUNCHED();
         const int below = np - j0 - 64;
         if (below > 0) {

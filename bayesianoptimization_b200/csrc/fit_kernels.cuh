@@ -3,6 +3,7 @@
 // log_marginal_likelihood (SK/gaussian_process/_gpr.py:349-367, :584-651).
 #pragma once
 #include "common.cuh"
+#include "potrf_block.cuh"
 
 namespace b200bo {
 
@@ -30,28 +31,39 @@ __global__ void scale_x_kernel(const double* __restrict__ X, const double* __res
 // K(X,X): full symmetric np x np matrix; K_ii = const + alpha; padding = identity.
 // (SK/gaussian_process/kernels.py:1716,1740-1743 + _gpr.py:350)
 // ---------------------------------------------------------------------------------------
-__global__ void kbuild_kernel(const double* __restrict__ Xs, double* __restrict__ K, int n, int np,
-                              int d, int family, int nu, double constv, double jitter) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= np || j >= np) return;
-    double v;
-    if (i >= n || j >= n) {
-        v = (i == j) ? 1.0 : 0.0;
-    } else if (i == j) {
-        v = constv + jitter;
-    } else {
-        // pdist order: row min(i,j) first; (a-b)^2 is symmetric so the value is too
-        const double* a = Xs + (size_t)min(i, j) * d;
-        const double* b = Xs + (size_t)max(i, j) * d;
-        double r2 = 0.0;
-        for (int t = 0; t < d; ++t) {
-            const double df = a[t] - b[t];
-            r2 += df * df;
-        }
-        v = constv * cov_from_r2(r2, family, nu);
+// 32x32 output tile per CTA (32x8 threads, 4 rows each); the two 32-row slabs of Xs are staged in
+// shared memory with coalesced loads (row stride 65: conflict-free when lanes walk different rows).
+__global__ void __launch_bounds__(256)
+kbuild_kernel(const double* __restrict__ Xs, double* __restrict__ K, int n, int np, int d, int family,
+              int nu, double constv, double jitter) {
+    __shared__ double xi[32][B200BO_MAX_DIM + 1], xj[32][B200BO_MAX_DIM + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+    const int j0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+    for (int idx = tid; idx < 32 * d; idx += 256) {
+        const int r = idx / d, t = idx - r * d;
+        xi[r][t] = Xs[(size_t)i0 * d + idx];
+        xj[r][t] = Xs[(size_t)j0 * d + idx];
     }
-    K[(size_t)i * np + j] = v;
+    __syncthreads();
+    const int j = j0 + tx;
+    for (int rr = ty; rr < 32; rr += 8) {
+        const int i = i0 + rr;
+        double v;
+        if (i >= n || j >= n) {
+            v = (i == j) ? 1.0 : 0.0;
+        } else if (i == j) {
+            v = constv + jitter;
+        } else {
+            // (a-b)^2 is symmetric, so K is too (pdist evaluates each pair once)
+            double r2 = 0.0;
+            for (int t = 0; t < d; ++t) {
+                const double df = xi[rr][t] - xj[tx][t];
+                r2 += df * df;
+            }
+            v = constv * cov_from_r2(r2, family, nu);
+        }
+        K[(size_t)i * np + j] = v;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -148,12 +160,70 @@ dgemm64_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, 
 
 // ---------------------------------------------------------------------------------------
 // Diagonal 64x64 block: in-place Cholesky (lower) + inverse of the factor written to Dinv.
+// Single CTA, 256 threads, phases in potrf_block.cuh (8-column panels: 3 barriers per panel
+// instead of 2 per column, one rsqrt per pivot instead of sqrt + divisions; inverse by recursive
+// doubling instead of 64 dependent substitution steps).  Agrees with the unblocked kernel below to
+// round-off.
+// info: 0 or the 1-based index of the first non-positive pivot (LAPACK dpotrf convention,
+// SP/linalg/_decomp_cholesky.py:58 raises LinAlgError on it).
+// ---------------------------------------------------------------------------------------
+constexpr int kPotrfSmemBytes = 3 * potrf::kB * potrf::kLd * 8;
+__global__ void __launch_bounds__(256)
+potrf_diag_kernel(double* A, int ld, int j0, double* Dinv, int ldd, int* info) {
+    using namespace potrf;
+    extern __shared__ __align__(16) double potrf_smem[];
+    double* S = potrf_smem;
+    double* V = potrf_smem + kB * kLd;
+    double* T = potrf_smem + 2 * kB * kLd;
+    __shared__ double diag[kB], rdiag[kB];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int idx = tid; idx < kB * kB; idx += kThreads) {
+        const int r = idx >> 6, c = idx & 63;
+        S[r * kLd + c] = A[(size_t)(j0 + r) * ld + j0 + c];
+        V[r * kLd + c] = 0.0;
+    }
+    __syncthreads();
+    for (int c0 = 0; c0 < kB; c0 += kPw) {
+        if (warp == 0) {
+            const int bad = diag_factor(S, diag, rdiag, c0);
+            if (bad != 0 && tid == 0 && *info == 0) *info = j0 + bad;
+        }
+        __syncthreads();
+        if (c0 + kPw < kB) {
+            panel_solve(tid, S, rdiag, c0);
+            __syncthreads();
+            trailing_update(tid, S, c0);
+            __syncthreads();
+        }
+    }
+    // factor back to global memory (strict upper part of the block zeroed)
+    for (int idx = tid; idx < kB * kB; idx += kThreads) {
+        const int r = idx >> 6, c = idx & 63;
+        A[(size_t)(j0 + r) * ld + j0 + c] = (c < r) ? S[r * kLd + c] : (c == r ? diag[r] : 0.0);
+    }
+    diag_inverse(S, rdiag, V, warp);  // 8 warps <-> 8 diagonal 8x8 blocks
+    __syncthreads();
+    for (int s = kPw, l2 = 3; s < kB; s *= 2, ++l2) {
+        inverse_level_t(tid, S, V, T, s, l2);
+        __syncthreads();
+        inverse_level_w(tid, V, T, s, l2);
+        __syncthreads();
+    }
+    for (int idx = tid; idx < kB * kB; idx += kThreads) {
+        const int r = idx >> 6, c = idx & 63;
+        Dinv[(size_t)r * ldd + c] = V[r * kLd + c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Diagonal 64x64 block, first version (kept for A/B runs: B200BO_POTRF=legacy): unblocked
+// column-by-column Cholesky (two barriers per column) + inverse by forward substitution.
 // Single CTA, 256 threads.  info: 0 or the 1-based index of the first non-positive pivot
 // (LAPACK dpotrf convention, SP/linalg/_decomp_cholesky.py:58 raises LinAlgError on it).
 // ---------------------------------------------------------------------------------------
-constexpr int kPotrfSmemBytes = 2 * 64 * 65 * 8;
+constexpr int kPotrfLegacySmemBytes = 2 * 64 * 65 * 8;
 __global__ void __launch_bounds__(256)
-potrf_diag_kernel(double* A, int ld, int j0, double* Dinv, int ldd, int* info) {
+potrf_diag_legacy_kernel(double* A, int ld, int j0, double* Dinv, int ldd, int* info) {
     extern __shared__ __align__(16) double potrf_smem[];
     double (*S)[65] = reinterpret_cast<double (*)[65]>(potrf_smem);
     double (*V)[65] = reinterpret_cast<double (*)[65]>(potrf_smem + 64 * 65);

@@ -494,5 +494,5 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
         mode, arg = self.__dict__.get("_b200_xform", ("device", None))
         return apply_transform(mode, arg, X)
 
-    def sample_y(self, X, n_samples=1, random_state=0):
-        raise NotImplementedError("sample_y needs return_cov; not on the accelerated path")
+    # sample_y (SK/gaussian_process/_gpr.py:502-539) is inherited: it only calls
+    # self.predict(X, return_cov=True), which runs on the device.

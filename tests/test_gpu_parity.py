@@ -70,6 +70,32 @@ def test_fit_state_vs_golden(bo, golden):
     assert float(gp._y_train_std) == pytest.approx(float(g["y_std"]), rel=1e-14)
 
 
+def test_blocked_diagonal_kernel_equals_unblocked(bo, monkeypatch):
+    """The 8-column-panel diagonal-block kernel (csrc/potrf_block.cuh; rsqrt pivots, inverse by
+    recursive doubling) against the first, unblocked kernel (B200BO_POTRF=legacy; sqrt + divisions,
+    inverse by substitution): factor, inverse and alpha_ agree to round-off."""
+    from bayesianoptimization_b200 import _lib as B
+
+    X, y = _synth(700, 5)
+    n = X.shape[0]
+    out = {}
+    for mode in ("blocked", "legacy"):
+        if mode == "legacy":
+            monkeypatch.setenv("B200BO_POTRF", "legacy")
+        else:
+            monkeypatch.delenv("B200BO_POTRF", raising=False)
+        gp = make_gp(bo, Matern(nu=2.5, length_scale=0.8)).fit(X, y)
+        W = np.empty((n, n))
+        B.check(B.lib().b200bo_gp_get(gp._handle().ptr, B.GET_LINV, B.as_dp(W), n * n))
+        out[mode] = (gp.L_.copy(), W, gp.alpha_.copy())
+    assert_allclose(out["blocked"][0][:64, :64], out["legacy"][0][:64, :64], rtol=1e-11, atol=1e-14)
+    assert_allclose(out["blocked"][0], out["legacy"][0], rtol=1e-8, atol=1e-12)
+    L = out["blocked"][0]
+    for mode in out:
+        assert np.max(np.abs(out[mode][1] @ L - np.eye(n))) < 1e-7, mode
+    assert_allclose(out["blocked"][2], out["legacy"][2], rtol=1e-7)
+
+
 @pytest.mark.parametrize("n", [1, 63, 64, 65, 127, 129, 200, 257, 700])
 def test_factor_padding_and_ragged_sizes(bo, O, n):
     rs = np.random.RandomState(n)
@@ -805,6 +831,24 @@ def test_predict_return_cov_vs_sklearn(bo, n, d, m):
     assert_allclose(np.sqrt(np.maximum(np.diag(c), 0)), gp.predict(xt, return_std=True)[1], rtol=1e-6, atol=1e-7)
     with pytest.raises(RuntimeError):
         gp.predict(xt, return_std=True, return_cov=True)
+
+
+def test_sample_y_uses_device_cov(bo):
+    """sample_y (SK/gaussian_process/_gpr.py:502-539) is sklearn's own code over the device
+    predict(return_cov=True): same draws as drawing from the device mean/cov directly, and close to
+    the live sklearn GPR's samples on a well-conditioned posterior."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+
+    X, y = _synth(60, 2)
+    xt = np.random.RandomState(4).uniform(size=(6, 2))
+    k = Matern(nu=2.5, length_scale=0.4)
+    gp = make_gp(bo, k).fit(X, y)
+    s = gp.sample_y(xt, n_samples=5, random_state=7)
+    assert s.shape == (6, 5)
+    mu, c = gp.predict(xt, return_cov=True)
+    assert_allclose(s, np.random.RandomState(7).multivariate_normal(mu, c, 5).T, rtol=1e-12, atol=1e-12)
+    ref = GaussianProcessRegressor(kernel=k, alpha=1e-6, normalize_y=True, optimizer=None).fit(X, y)
+    assert_allclose(s, ref.sample_y(xt, n_samples=5, random_state=7), rtol=1e-4, atol=1e-6)
 
 
 def test_incremental_append_equals_full_fit(bo, O):

@@ -302,3 +302,21 @@ def test_bench_reference_arm_contract():
         assert key in j, key
     assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port"
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in j["config"]
+
+
+def test_potrf_block_emulation(tmp_path):
+    """The diagonal-block Cholesky kernel's phases (csrc/potrf_block.cuh) are host/device functions;
+    tools/potrf_emul.cpp runs them sequentially on the CPU: factor bit-identical to the unblocked
+    algorithm, no intra-phase ordering hazards, inverse at round-off, LAPACK-style pivot index."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    exe = str(tmp_path / "potrf_emul")
+    subprocess.run([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-o", exe,
+                    os.path.join(ROOT, "tools", "potrf_emul.cpp")], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert out.stdout.count(" ok") == 6
