@@ -21,7 +21,8 @@ PRECISION_FP64, PRECISION_FP32 = 0, 1
 
 EXPORTS = [
     "b200bo_version", "b200bo_last_error", "b200bo_device_count", "b200bo_launch_count",
-    "b200bo_gp_create", "b200bo_gp_destroy", "b200bo_gp_set_precision", "b200bo_gp_set_transform", "b200bo_gp_fit",
+    "b200bo_gp_create", "b200bo_gp_destroy", "b200bo_gp_set_precision", "b200bo_gp_set_private_stream",
+    "b200bo_gp_set_transform", "b200bo_gp_fit",
     "b200bo_gp_set_data", "b200bo_gp_append", "b200bo_gp_lml", "b200bo_gp_get", "b200bo_gp_n", "b200bo_gp_dim",
     "b200bo_gp_predict", "b200bo_gp_predict_cov", "b200bo_acq_eval", "b200bo_acq_argmin_topk", "b200bo_acq_eval_dev",
     "b200bo_last_kernel_ms",
@@ -73,6 +74,7 @@ def lib():
     L.b200bo_gp_destroy.argtypes = [C.c_void_p]
     L.b200bo_gp_destroy.restype = None
     L.b200bo_gp_set_precision.argtypes = [C.c_void_p, C.c_int]
+    L.b200bo_gp_set_private_stream.argtypes = [C.c_void_p, C.c_int]
     L.b200bo_gp_set_transform.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int]
     L.b200bo_gp_fit.argtypes = [C.c_void_p, dp, dp, C.c_int64, C.c_int, C.POINTER(KernelSpec),
                                 C.c_double, C.c_int, i64p]

@@ -92,9 +92,40 @@ struct b200bo_gp {
     DevBuf cov_xc, cov_kst, cov_v, cov_c, cov_out, cov_mu;  // predict(return_cov=True) scratch
     int precision = B200BO_PRECISION_FP64;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // fit-side work (set_data / fit / lml) of this handle is issued on this stream: the legacy default
+    // stream (nullptr) unless b200bo_gp_set_private_stream gave the handle its own, so that several
+    // handles driven from different host threads factorise concurrently
+    cudaStream_t stream = nullptr;
+};
+
+// stream of the fit-side entry point in flight on this thread
+static thread_local cudaStream_t g_st = nullptr;
+struct StreamScope {
+    cudaStream_t prev;
+    explicit StreamScope(const b200bo_gp* gp) : prev(g_st) { g_st = gp ? gp->stream : nullptr; }
+    ~StreamScope() { g_st = prev; }
 };
 
 static thread_local b200bo_gp* g_last_timed = nullptr;
+
+// wait for the fit-side stream (the whole device when it is the legacy default stream)
+static int sync_fit_stream() {
+    if (g_st)
+        CU(cudaStreamSynchronize(g_st));
+    else
+        CU(cudaDeviceSynchronize());
+    return B200BO_OK;
+}
+// host <-> device copies ordered in the fit-side stream; d2h returns with the data on the host
+static int h2d(void* dst, const void* src, size_t bytes) {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_st));
+    return B200BO_OK;
+}
+static int d2h(void* dst, const void* src, size_t bytes) {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_st));
+    CU(cudaStreamSynchronize(g_st));
+    return B200BO_OK;
+}
 
 static inline int round_up(long long v, int m) { return (int)(((v + m - 1) / m) * m); }
 
@@ -113,9 +144,7 @@ extern "C" int b200bo_device_count(void) {
 
 // device properties, timing events and the opt-in shared-memory sizes of the big kernels
 static int init_handle(b200bo_gp* gp) {
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, gp->device));
-    gp->sm_count = prop.multiProcessorCount;
+    CU(cudaDeviceGetAttribute(&gp->sm_count, cudaDevAttrMultiProcessorCount, gp->device));
     CU(cudaEventCreate(&gp->ev0));
     CU(cudaEventCreate(&gp->ev1));
     CU(cudaFuncSetAttribute(predict_acq_kernel<PREDICT_IMPL_DFMA, false>,
@@ -171,6 +200,7 @@ extern "C" void b200bo_gp_destroy(b200bo_gp* gp) {
                       &gp->clamp, &gp->s_ksm, &gp->s_partial, &gp->s_mupart, &gp->s_unit, &gp->s_rb,
                       &gp->tc_linv, &gp->cov_xc, &gp->cov_kst, &gp->cov_v, &gp->cov_c, &gp->cov_out, &gp->cov_mu};
     for (DevBuf* b : bufs) b->release();
+    if (gp->stream) cudaStreamDestroy(gp->stream);
     if (gp->ev0) cudaEventDestroy(gp->ev0);
     if (gp->ev1) cudaEventDestroy(gp->ev1);
     if (g_last_timed == gp) g_last_timed = nullptr;
@@ -185,6 +215,19 @@ extern "C" int b200bo_gp_set_precision(b200bo_gp* gp, int precision) {
     if (precision != B200BO_PRECISION_FP64 && precision != B200BO_PRECISION_FP32)
         return set_err(B200BO_ERR_ARG, "unknown precision %d", precision);
     gp->precision = precision;
+    return B200BO_OK;
+}
+
+extern "C" int b200bo_gp_set_private_stream(b200bo_gp* gp, int enable) {
+    if (!gp) return set_err(B200BO_ERR_ARG, "gp is NULL");
+    CU(cudaSetDevice(gp->device));
+    if (enable && !gp->stream) {
+        CU(cudaStreamCreate(&gp->stream));  // a blocking stream: still ordered against legacy-stream work
+    } else if (!enable && gp->stream) {
+        CU(cudaStreamSynchronize(gp->stream));
+        CU(cudaStreamDestroy(gp->stream));
+        gp->stream = nullptr;
+    }
     return B200BO_OK;
 }
 
@@ -215,6 +258,7 @@ extern "C" int b200bo_gp_set_data(b200bo_gp* gp, const double* X, const double* 
     if (!gp->xform.empty() && (int)gp->xform.size() != d)
         return set_err(B200BO_ERR_ARG, "transform has %zu entries, d=%d", gp->xform.size(), d);
     CU(cudaSetDevice(gp->device));
+    StreamScope scope(gp);
     gp->fitted = false;
     gp->tc_valid = false;
     gp->n = n;
@@ -258,11 +302,11 @@ extern "C" int b200bo_gp_set_data(b200bo_gp* gp, const double* X, const double* 
     if ((rc = gp->W.reserve(sizeof(double) * np * np))) return rc;
     if ((rc = gp->WT.reserve(sizeof(double) * np * np))) return rc;
     if ((rc = gp->T.reserve(sizeof(double) * np * np))) return rc;
-    CU(cudaMemcpy(gp->X.p, X, sizeof(double) * n * d, cudaMemcpyHostToDevice));
-    CU(cudaMemset(gp->y.p, 0, sizeof(double) * np));
-    CU(cudaMemcpy(gp->y.p, gp->y_norm.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
-    if (!gp->xform.empty())
-        CU(cudaMemcpy(gp->xf.p, gp->xform.data(), sizeof(int) * d, cudaMemcpyHostToDevice));
+    if ((rc = h2d(gp->X.p, X, sizeof(double) * n * d))) return rc;
+    CU(cudaMemsetAsync(gp->y.p, 0, sizeof(double) * np, g_st));
+    if ((rc = h2d(gp->y.p, gp->y_norm.data(), sizeof(double) * n))) return rc;
+    if (!gp->xform.empty() && (rc = h2d(gp->xf.p, gp->xform.data(), sizeof(int) * d))) return rc;
+    if ((rc = sync_fit_stream())) return rc;  // the caller may release X / y on return
     gp->has_data = true;
     return B200BO_OK;
 }
@@ -287,7 +331,7 @@ static int gemm(int M, int N, int K, double alpha, const double* A, int lda, lon
                 long long sC, int batch, int lower_only, int kmode) {
     if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return B200BO_OK;
     dim3 grid(N / 64, M / 64, batch);
-    dgemm64_kernel<TA, TB><<<grid, 256>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC,
+    dgemm64_kernel<TA, TB><<<grid, 256, 0, g_st>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC,
                                           lower_only, kmode);
     LAUNCHED();
     CU(cudaGetLastError());
@@ -300,17 +344,18 @@ static int factorize(b200bo_gp* gp, const b200bo_kernel* kern, double jitter, in
     const int n = (int)gp->n, np = gp->np, d = gp->d;
     double ls[B200BO_MAX_DIM];
     for (int j = 0; j < d; ++j) ls[j] = kern->length_scale[kern->n_length_scale == 1 ? 0 : j];
-    CU(cudaMemcpy(gp->ls.p, ls, sizeof(double) * d, cudaMemcpyHostToDevice));
+    int rc;
+    if ((rc = h2d(gp->ls.p, ls, sizeof(double) * d))) return rc;
     const int* xf = gp->xform.empty() ? nullptr : gp->xf.as<int>();
     {
         const long long tot = (long long)np * d;
-        scale_x_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(gp->X.as<double>(), gp->ls.as<double>(), xf,
+        scale_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, g_st>>>(gp->X.as<double>(), gp->ls.as<double>(), xf,
                                                                gp->Xs.as<double>(), n, np, d);
         LAUNCHED();
     }
     {
         dim3 blk(32, 8), grd(np / 32, np / 32);
-        kbuild_kernel<<<grd, blk>>>(gp->Xs.as<double>(), gp->K.as<double>(), n, np, d, kern->family,
+        kbuild_kernel<<<grd, blk, 0, g_st>>>(gp->Xs.as<double>(), gp->K.as<double>(), n, np, d, kern->family,
                                     kern->family == B200BO_KERNEL_RBF ? B200BO_NU_INF : kern->nu,
                                     kern->const_value, jitter);
         LAUNCHED();
@@ -319,20 +364,19 @@ static int factorize(b200bo_gp* gp, const b200bo_kernel* kern, double jitter, in
     double* L = gp->L.as<double>();
     double* W = gp->W.as<double>();
     double* T = gp->T.as<double>();
-    CU(cudaMemcpyAsync(L, gp->K.p, sizeof(double) * (size_t)np * np, cudaMemcpyDeviceToDevice));
-    CU(cudaMemsetAsync(W, 0, sizeof(double) * (size_t)np * np));
-    CU(cudaMemsetAsync(gp->info.p, 0, sizeof(int)));
-    int rc;
+    CU(cudaMemcpyAsync(L, gp->K.p, sizeof(double) * (size_t)np * np, cudaMemcpyDeviceToDevice, g_st));
+    CU(cudaMemsetAsync(W, 0, sizeof(double) * (size_t)np * np, g_st));
+    CU(cudaMemsetAsync(gp->info.p, 0, sizeof(int), g_st));
     // right-looking blocked Cholesky, panel width 64.  B200BO_POTRF=legacy selects the first
     // (unblocked) diagonal-block kernel for A/B measurements; the factor is bit-identical.
     const char* pv = getenv("B200BO_POTRF");
     const bool legacy_potrf = pv && (pv[0] == 'l' || pv[0] == 'L');
     for (int j0 = 0; j0 < np; j0 += 64) {
         if (legacy_potrf)
-            potrf_diag_legacy_kernel<<<1, 256, kPotrfLegacySmemBytes>>>(L, np, j0, W + (size_t)j0 * np + j0, np,
+            potrf_diag_legacy_kernel<<<1, 256, kPotrfLegacySmemBytes, g_st>>>(L, np, j0, W + (size_t)j0 * np + j0, np,
                                                                         gp->info.as<int>());
         else
-            potrf_diag_kernel<<<1, 256, kPotrfSmemBytes>>>(L, np, j0, W + (size_t)j0 * np + j0, np,
+            potrf_diag_kernel<<<1, 256, kPotrfSmemBytes, g_st>>>(L, np, j0, W + (size_t)j0 * np + j0, np,
                                                            gp->info.as<int>());
         LAUNCHED();
         const int below = np - j0 - 64;
@@ -350,11 +394,11 @@ static int factorize(b200bo_gp* gp, const b200bo_kernel* kern, double jitter, in
     }
     {
         dim3 blk(32, 8), grd((np + 31) / 32, (np + 7) / 8);
-        zero_upper_kernel<<<grd, blk>>>(L, np);
+        zero_upper_kernel<<<grd, blk, 0, g_st>>>(L, np);
         LAUNCHED();
     }
     int info = 0;
-    CU(cudaMemcpy(&info, gp->info.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if ((rc = d2h(&info, gp->info.p, sizeof(int)))) return rc;
     *info_out = info;
     if (info != 0) return B200BO_OK;
     // W = L^-1 by recursive doubling over diagonal blocks:
@@ -394,7 +438,7 @@ static int factorize(b200bo_gp* gp, const b200bo_kernel* kern, double jitter, in
 static int transpose_W(b200bo_gp* gp) {
     const int np = gp->np;
     dim3 blk(32, 8), grd(np / 32, np / 32);
-    transpose_kernel<<<grd, blk>>>(gp->W.as<double>(), gp->WT.as<double>(), np);
+    transpose_kernel<<<grd, blk, 0, g_st>>>(gp->W.as<double>(), gp->WT.as<double>(), np);
     LAUNCHED();
     CU(cudaGetLastError());
     return B200BO_OK;
@@ -410,14 +454,14 @@ static int solve_alpha(b200bo_gp* gp) {
     double* v2 = gp->v2.as<double>();
     const double* y = gp->y.as<double>();
     // z = W y ; a = W^T z
-    gemv_rows_kernel<<<grd, blk>>>(gp->W.as<double>(), np, y, v1, np, np, 1);
-    gemv_rows_kernel<<<grd, blk>>>(gp->WT.as<double>(), np, v1, a, np, np, 2);
+    gemv_rows_kernel<<<grd, blk, 0, g_st>>>(gp->W.as<double>(), np, y, v1, np, np, 1);
+    gemv_rows_kernel<<<grd, blk, 0, g_st>>>(gp->WT.as<double>(), np, v1, a, np, np, 2);
     // r = y - K a ; a += W^T W r
-    gemv_rows_kernel<<<grd, blk>>>(gp->K.as<double>(), np, a, v1, np, np, 0);
-    residual_kernel<<<(np + 255) / 256, 256>>>(y, v1, np);
-    gemv_rows_kernel<<<grd, blk>>>(gp->W.as<double>(), np, v1, v2, np, np, 1);
-    gemv_rows_kernel<<<grd, blk>>>(gp->WT.as<double>(), np, v2, v1, np, np, 2);
-    axpy1_kernel<<<(np + 255) / 256, 256>>>(a, v1, np);
+    gemv_rows_kernel<<<grd, blk, 0, g_st>>>(gp->K.as<double>(), np, a, v1, np, np, 0);
+    residual_kernel<<<(np + 255) / 256, 256, 0, g_st>>>(y, v1, np);
+    gemv_rows_kernel<<<grd, blk, 0, g_st>>>(gp->W.as<double>(), np, v1, v2, np, np, 1);
+    gemv_rows_kernel<<<grd, blk, 0, g_st>>>(gp->WT.as<double>(), np, v2, v1, np, np, 2);
+    axpy1_kernel<<<(np + 255) / 256, 256, 0, g_st>>>(a, v1, np);
     for (int i = 0; i < 7; ++i) LAUNCHED();
     CU(cudaGetLastError());
     return B200BO_OK;
@@ -428,6 +472,7 @@ extern "C" int b200bo_gp_fit(b200bo_gp* gp, const double* X, const double* y, in
     int rc;
     if ((rc = b200bo_gp_set_data(gp, X, y, n, d, normalize_y))) return rc;
     if ((rc = check_kernel(gp, kern))) return rc;
+    StreamScope scope(gp);
     if (info) *info = 0;
     int finfo = 0;
     if ((rc = factorize(gp, kern, alpha, &finfo))) return rc;
@@ -437,7 +482,7 @@ extern "C" int b200bo_gp_fit(b200bo_gp* gp, const double* X, const double* y, in
     }
     if ((rc = transpose_W(gp))) return rc;
     if ((rc = solve_alpha(gp))) return rc;
-    CU(cudaDeviceSynchronize());
+    if ((rc = sync_fit_stream())) return rc;
     gp->family = kern->family;
     gp->nu = kern->family == B200BO_KERNEL_RBF ? B200BO_NU_INF : kern->nu;
     gp->constv = kern->const_value;
@@ -519,6 +564,7 @@ extern "C" int b200bo_gp_lml(b200bo_gp* gp, const b200bo_kernel* kern, double al
     int rc;
     if ((rc = check_kernel(gp, kern))) return rc;
     CU(cudaSetDevice(gp->device));
+    StreamScope scope(gp);
     gp->fitted = false;  // buffers are being overwritten
     gp->tc_valid = false;
     const int n = (int)gp->n, np = gp->np, d = gp->d;
@@ -534,11 +580,11 @@ extern "C" int b200bo_gp_lml(b200bo_gp* gp, const b200bo_kernel* kern, double al
     }
     if ((rc = transpose_W(gp))) return rc;
     if ((rc = solve_alpha(gp))) return rc;
-    diag_kernel<<<(n + 255) / 256, 256>>>(gp->L.as<double>(), np, gp->v1.as<double>(), n);
+    diag_kernel<<<(n + 255) / 256, 256, 0, g_st>>>(gp->L.as<double>(), np, gp->v1.as<double>(), n);
     LAUNCHED();
     std::vector<double> a(n), dg(n);
-    CU(cudaMemcpy(a.data(), gp->alphav.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(dg.data(), gp->v1.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if ((rc = d2h(a.data(), gp->alphav.p, sizeof(double) * n))) return rc;
+    if ((rc = d2h(dg.data(), gp->v1.p, sizeof(double) * n))) return rc;
     long double ya = 0.0L, ld = 0.0L;
     for (int i = 0; i < n; ++i) {
         ya += (long double)gp->y_norm[i] * a[i];
@@ -553,14 +599,14 @@ extern "C" int b200bo_gp_lml(b200bo_gp* gp, const b200bo_kernel* kern, double al
         dim3 grd((n + 15) / 16, (n + 15) / 16);
         const size_t nblk = (size_t)grd.x * grd.y;
         if ((rc = gp->part.reserve(sizeof(double) * nblk * ntheta))) return rc;
-        lml_grad_kernel<<<grd, 256>>>(gp->Xs.as<double>(), gp->T.as<double>(), np, gp->alphav.as<double>(),
+        lml_grad_kernel<<<grd, 256, 0, g_st>>>(gp->Xs.as<double>(), gp->T.as<double>(), np, gp->alphav.as<double>(),
                                       n, d, kern->family,
                                       kern->family == B200BO_KERNEL_RBF ? B200BO_NU_INF : kern->nu,
                                       kern->const_value, has_const, aniso, gp->part.as<double>(), ntheta);
         LAUNCHED();
         CU(cudaGetLastError());
         std::vector<double> part(nblk * ntheta);
-        CU(cudaMemcpy(part.data(), gp->part.p, sizeof(double) * nblk * ntheta, cudaMemcpyDeviceToHost));
+        if ((rc = d2h(part.data(), gp->part.p, sizeof(double) * nblk * ntheta))) return rc;
         for (int p = 0; p < ntheta; ++p) {
             long double s = 0.0L;
             for (size_t b = 0; b < nblk; ++b) s += part[b * ntheta + p];

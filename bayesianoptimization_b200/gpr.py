@@ -12,6 +12,8 @@ ImportError, a missing device raises B200Error.
 from __future__ import annotations
 
 import ctypes as C
+import os
+import threading
 import warnings
 from operator import itemgetter
 
@@ -214,6 +216,7 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
         state = super().__getstate__() if hasattr(super(), "__getstate__") else self.__dict__.copy()
         state = dict(state)
         state.pop("_b200_handle", None)
+        state.pop("_b200_restart_handles", None)
         state["_b200_device_fitted"] = False
         return state
 
@@ -336,21 +339,31 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
             B.check(L.b200bo_gp_set_data(h.ptr, B.as_dp(Xd), B.as_dp(B.c_f64(y)), Xd.shape[0], Xd.shape[1],
                                          int(bool(self.normalize_y))))
 
-            def obj_func(theta, eval_gradient=True):
-                if eval_gradient:
-                    lml, grad = self._device_lml(ek.with_theta(theta), True)
-                    return -lml, -grad
-                return -self._device_lml(ek.with_theta(theta), False)
+            def make_obj(handle):
+                def obj_func(theta, eval_gradient=True):
+                    if eval_gradient:
+                        lml, grad = self._device_lml(ek.with_theta(theta), True, handle)
+                        return -lml, -grad
+                    return -self._device_lml(ek.with_theta(theta), False, handle)
 
-            optima = [self._constrained_optimization(obj_func, self.kernel_.theta, self.kernel_.bounds)]
+                return obj_func
+
+            # the 1 + n_restarts_optimizer starting points (:321-340); the restarts' thetas are drawn
+            # from self._rng in the reference's order - the draws do not depend on the optimisations
+            bounds = self.kernel_.bounds
+            starts = [self.kernel_.theta]
             if self.n_restarts_optimizer > 0:
-                if not np.isfinite(self.kernel_.bounds).all():
+                if not np.isfinite(bounds).all():
                     raise ValueError("Multiple optimizer restarts (n_restarts_optimizer>0) "
                                      "requires that all bounds are finite.")
-                bounds = self.kernel_.bounds
                 for _ in range(self.n_restarts_optimizer):
-                    theta_initial = self._rng.uniform(bounds[:, 0], bounds[:, 1])
-                    optima.append(self._constrained_optimization(obj_func, theta_initial, bounds))
+                    starts.append(self._rng.uniform(bounds[:, 0], bounds[:, 1]))
+            workers = self._restart_workers(len(starts), Xd, y, codes)
+            if workers is None:
+                obj_func = make_obj(h)
+                optima = [self._constrained_optimization(obj_func, t0, bounds) for t0 in starts]
+            else:
+                optima = self._run_restarts_concurrently(workers, make_obj, starts, bounds)
             lml_values = list(map(itemgetter(1), optima))
             self.kernel_.theta = optima[np.argmin(lml_values)][0]
             self.kernel_._check_bounds_params()
@@ -362,6 +375,72 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
                 self._device_fit(ek)
             self.log_marginal_likelihood_value_ = None  # computed on demand (costs one more factorisation)
         return self
+
+    # ---- concurrent restarts -----------------------------------------------------------------
+    _MAX_RESTART_WORKERS = 8
+    _RESTART_POOL_BYTES = 24 << 30
+    _RESTART_MIN_N = 192  # below this an LML evaluation is ~0.3 ms: worker handles cost more than they save
+
+    def _restart_workers(self, n_starts, Xd, y, codes):
+        """Handles for running the independent L-BFGS-B starts concurrently (one host thread + one
+        CUDA stream + one set of factor buffers each), or None for the sequential loop.  An LML
+        evaluation at these sizes is a chain of ~200 dependent launches that leaves most SMs idle;
+        several chains in flight fill them.  Every run sees exactly the objective values it would see
+        alone, so the optima are those of the sequential loop.  B200BO_PARALLEL_RESTARTS=0 disables."""
+        if n_starts < 2 or self.optimizer != "fmin_l_bfgs_b" or Xd.shape[0] < self._RESTART_MIN_N:
+            return None
+        if os.environ.get("B200BO_PARALLEL_RESTARTS", "1") == "0":
+            return None
+        n_workers = min(n_starts, self._MAX_RESTART_WORKERS)
+        npad = -(-Xd.shape[0] // 128) * 128
+        if (n_workers - 1) * 5 * 8 * npad * npad > self._RESTART_POOL_BYTES:
+            return None
+        L = B.lib()
+        pool = self.__dict__.setdefault("_b200_restart_handles", [])
+        while len(pool) < n_workers - 1:
+            pool.append(_Handle(self.device))
+        handles = [self._handle()] + pool[:n_workers - 1]
+        yc = B.c_f64(y)
+        for i, hd in enumerate(handles):
+            B.check(L.b200bo_gp_set_private_stream(hd.ptr, 1))
+            if i == 0:
+                continue  # the main handle already holds the data
+            B.check(L.b200bo_gp_set_transform(
+                hd.ptr, codes.ctypes.data_as(C.POINTER(C.c_int32)) if codes is not None else None, Xd.shape[1]))
+            B.check(L.b200bo_gp_set_data(hd.ptr, B.as_dp(Xd), B.as_dp(yc), Xd.shape[0], Xd.shape[1],
+                                         int(bool(self.normalize_y))))
+        return handles
+
+    def _run_restarts_concurrently(self, handles, make_obj, starts, bounds):
+        results, errors = [None] * len(starts), []
+        lock = threading.Lock()
+        nxt = [0]
+
+        def work(handle):
+            obj = make_obj(handle)
+            while True:
+                with lock:
+                    i = nxt[0]
+                    nxt[0] += 1
+                if i >= len(starts) or errors:
+                    return
+                try:
+                    results[i] = self._constrained_optimization(obj, starts[i], bounds)
+                except BaseException as e:  # re-raised in the calling thread
+                    errors.append(e)
+                    return
+
+        threads = [threading.Thread(target=work, args=(hd,), daemon=True) for hd in handles]
+        try:
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+        finally:
+            B.lib().b200bo_gp_set_private_stream(handles[0].ptr, 0)  # main handle back on the default stream
+        if errors:
+            raise errors[0]
+        return results
 
     def _try_incremental(self, prev, X, y, ek):
         """Fixed hyper-parameters (optimizer=None) and the new training set = the previous one plus
@@ -407,8 +486,8 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
             return self.optimizer(obj_func, initial_theta, bounds=bounds)
         raise ValueError(f"Unknown optimizer {self.optimizer}.")
 
-    def _device_lml(self, ek: EngineKernel, eval_gradient):
-        h = self._handle()
+    def _device_lml(self, ek: EngineKernel, eval_gradient, handle=None):
+        h = handle if handle is not None else self._handle()
         spec = ek.c_spec()
         lml = C.c_double(0.0)
         ntheta_dev = (1 if ek.const_free else 0) + ek.length_scale.size

@@ -109,6 +109,13 @@ void b200bo_gp_destroy(b200bo_gp* gp);
 #define B200BO_PRECISION_FP32 1
 int b200bo_gp_set_precision(b200bo_gp* gp, int precision);
 
+/* enable != 0: the handle's fit-side work (set_data / fit / lml) is issued on a CUDA stream of its own
+ * instead of the legacy default stream, so that several handles driven from different host threads
+ * factorise concurrently - the independent L-BFGS-B restarts of the hyper-parameter search
+ * (SK/gaussian_process/_gpr.py:321-340 runs them one after the other).  Every entry point still returns
+ * with its results complete; handles are not thread-safe individually (one thread per handle). */
+int b200bo_gp_set_private_stream(b200bo_gp* gp, int enable);
+
 /* Optional per-dimension input transform (wrap_kernel); xform has d entries or NULL. Must be
  * set before fit.  Replaces R/bayes_opt/parameter.py:484-487 for float/int parameters. */
 int b200bo_gp_set_transform(b200bo_gp* gp, const int32_t* xform, int d);

@@ -70,6 +70,34 @@ def test_fit_state_vs_golden(bo, golden):
     assert float(gp._y_train_std) == pytest.approx(float(g["y_std"]), rel=1e-14)
 
 
+@pytest.mark.parametrize("n,d,aniso", [(300, 3, False), (900, 4, True)])
+def test_concurrent_restarts_equal_sequential(bo, monkeypatch, n, d, aniso):
+    """The 1 + n_restarts L-BFGS-B runs of fit() (SK/gaussian_process/_gpr.py:321-340) run concurrently
+    (one thread + CUDA stream + factor buffers each).  Every LML evaluation is deterministic and
+    independent of what else is in flight, so theta and the LML must be BIT-identical to the sequential
+    loop (B200BO_PARALLEL_RESTARTS=0), and the RandomState must end in the same state."""
+    X, y = _synth(n, d)
+    ls = np.full(d, 0.7) if aniso else 0.7
+    out = {}
+    for mode in ("concurrent", "sequential", "concurrent")[:2 if aniso else 3]:
+        monkeypatch.setenv("B200BO_PARALLEL_RESTARTS", "0" if mode == "sequential" else "1")
+        rs = np.random.RandomState(5)
+        gp = bo.B200GaussianProcessRegressor(kernel=ConstantKernel(1.0) * Matern(nu=2.5, length_scale=ls), alpha=1e-6,
+                                             normalize_y=True, n_restarts_optimizer=4, random_state=rs)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            gp.fit(X, y)
+        res = (gp.kernel_.theta.copy(), gp.log_marginal_likelihood_value_, rs.uniform(), gp.predict(X[:5]))
+        if mode in out:
+            ref = out[mode]
+            assert np.array_equal(ref[0], res[0]) and ref[1] == res[1]
+        out[mode] = res
+    a, b = out["concurrent"], out["sequential"]
+    assert np.array_equal(a[0], b[0])
+    assert a[1] == b[1] and a[2] == b[2]
+    assert np.array_equal(a[3], b[3])
+
+
 def test_blocked_diagonal_kernel_equals_unblocked(bo, monkeypatch):
     """The 8-column-panel diagonal-block kernel (csrc/potrf_block.cuh; rsqrt pivots, inverse by
     recursive doubling) against the first, unblocked kernel (B200BO_POTRF=legacy; sqrt + divisions,
