@@ -320,3 +320,40 @@ def test_potrf_block_emulation(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert out.stdout.count(" ok") == 6
+
+
+def test_concurrent_restart_queue_order_and_errors():
+    """gpr._run_restarts_concurrently: results are stored by start index whatever thread ran them, and
+    the first exception of a worker is re-raised in the caller (no GPU: fake handles, fake optimiser)."""
+    import threading
+    import time
+
+    from bayesianoptimization_b200.gpr import B200GaussianProcessRegressor
+
+    class FakeHandle:
+        ptr = None
+
+    gp = B200GaussianProcessRegressor.__new__(B200GaussianProcessRegressor)
+    seen = []
+
+    def fake_opt(obj, theta0, bounds):
+        time.sleep(0.002 * (5 - theta0[0]))  # later starts finish first
+        seen.append(threading.get_ident())
+        return np.array([theta0[0] * 2.0]), obj(theta0)
+
+    gp._constrained_optimization = fake_opt
+    starts = [np.array([float(i)]) for i in range(5)]
+    res = gp._run_restarts_concurrently([FakeHandle(), FakeHandle(), FakeHandle()], lambda h: (lambda t: -t[0]),
+                                        starts, None)
+    assert [r[0][0] for r in res] == [0.0, 2.0, 4.0, 6.0, 8.0]
+    assert [r[1] for r in res] == [-0.0, -1.0, -2.0, -3.0, -4.0]
+    assert len(set(seen)) > 1
+
+    def failing(obj, theta0, bounds):
+        if theta0[0] == 1.0:
+            raise np.linalg.LinAlgError("boom")
+        return theta0, 0.0
+
+    gp._constrained_optimization = failing
+    with pytest.raises(np.linalg.LinAlgError):
+        gp._run_restarts_concurrently([FakeHandle(), FakeHandle()], lambda h: (lambda t: 0.0), starts, None)
