@@ -19,7 +19,6 @@ import warnings
 from copy import deepcopy
 
 import numpy as np
-from numpy.random import RandomState
 from packaging import version
 from scipy import __version__ as scipy_version
 from scipy.optimize import minimize
