@@ -4,28 +4,39 @@ behind ``bayes_opt.BayesianOptimization.suggest()`` and the ``bayes_opt.acquisit
 Hot path: GP fit -> batched posterior predict -> UCB/EI/PoI (x constraint probability) ->
 argmin/top-k, in hand-written sm_100a CUDA behind the C ABI declared in include/b200bo.h.
 No CPU fallback: importing the compute classes without the built library raises ImportError.
+
+Two layers:
+  * GP seam / C ABI (needs numpy, scipy, sklearn):  B200GaussianProcessRegressor, FusedAcquisition
+  * acquisition seam (a plug-in for the ``bayes_opt`` package, which must be importable):
+    UpperConfidenceBound, ExpectedImprovement, ProbabilityOfImprovement, ConstantLiar, GPHedge,
+    AcquisitionFunction, ConstraintModel, enable(optimizer) - resolved lazily on first access.
 """
 from . import _lib
 from ._build import build_library
-from .acquisition import (
-    AcquisitionFunction,
-    ConstantLiar,
-    ExpectedImprovement,
-    FusedAcquisition,
-    GPHedge,
-    ProbabilityOfImprovement,
-    UpperConfidenceBound,
-)
-from .constraint import ConstraintModel
-from .dropin import accelerate_acquisition, enable, to_b200_gp
-from .gpr import B200GaussianProcessRegressor
-from .space import TargetSpace
+from .dropin import accelerate_acquisition, enable
+from .fused import FusedAcquisition
+from .gpr import B200GaussianProcessRegressor, to_b200_gp
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
+
+_PLUGIN = {
+    "AcquisitionFunction": "acquisition", "UpperConfidenceBound": "acquisition",
+    "ExpectedImprovement": "acquisition", "ProbabilityOfImprovement": "acquisition",
+    "ConstantLiar": "acquisition", "GPHedge": "acquisition", "DeviceHooks": "acquisition",
+    "ConstraintModel": "constraint",
+}
+
+
+def __getattr__(name):
+    mod = _PLUGIN.get(name)
+    if mod is None:
+        raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+    import importlib
+
+    return getattr(importlib.import_module(f"{__name__}.{mod}"), name)
+
 
 __all__ = [
-    "AcquisitionFunction", "ConstantLiar", "ExpectedImprovement", "FusedAcquisition", "GPHedge",
-    "ProbabilityOfImprovement", "UpperConfidenceBound", "ConstraintModel",
-    "B200GaussianProcessRegressor", "TargetSpace", "enable", "accelerate_acquisition",
-    "to_b200_gp", "build_library", "__version__",
+    "B200GaussianProcessRegressor", "FusedAcquisition", "enable", "accelerate_acquisition", "to_b200_gp",
+    "build_library", "__version__", *_PLUGIN,
 ]

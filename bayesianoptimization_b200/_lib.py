@@ -18,6 +18,7 @@ MAX_GPS, MAX_DIM, MAX_TOPK = 8, 64, 64
 XFORM_IDENTITY, XFORM_ROUND = 0, 1
 GET_L, GET_ALPHA, GET_YSTATS, GET_K, GET_LINV = 0, 1, 2, 3, 4
 PRECISION_FP64, PRECISION_FP32 = 0, 1
+PATH_AUTO, PATH_STABLE = 0, 1
 
 EXPORTS = [
     "b200bo_version", "b200bo_last_error", "b200bo_device_count", "b200bo_launch_count",
@@ -26,6 +27,9 @@ EXPORTS = [
     "b200bo_gp_set_data", "b200bo_gp_append", "b200bo_gp_lml", "b200bo_gp_get", "b200bo_gp_n", "b200bo_gp_dim",
     "b200bo_gp_predict", "b200bo_gp_predict_cov", "b200bo_acq_eval", "b200bo_acq_argmin_topk", "b200bo_acq_eval_dev",
     "b200bo_last_kernel_ms",
+    "b200bo_acq_argmin_topk_philox", "b200bo_acq_select_philox_dev", "b200bo_philox_rows",
+    "b200bo_gp_replicate", "b200bo_multi_gpu_acq_argmin_topk", "b200bo_multi_gpu_acq_argmin_topk_philox",
+    "b200bo_multi_gpu_acq_eval",
 ]
 
 
@@ -39,7 +43,8 @@ class KernelSpec(C.Structure):
 
 class AcqSpec(C.Structure):
     _fields_ = [
-        ("kind", C.c_int32), ("n_gps", C.c_int32), ("kappa", C.c_double), ("xi", C.c_double),
+        ("kind", C.c_int32), ("n_gps", C.c_int32), ("path", C.c_int32), ("reserved", C.c_int32),
+        ("kappa", C.c_double), ("xi", C.c_double),
         ("y_max", C.c_double), ("gps", C.c_void_p * MAX_GPS), ("lb", C.c_double * MAX_GPS),
         ("ub", C.c_double * MAX_GPS),
     ]
@@ -94,6 +99,18 @@ def lib():
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
                                       C.c_void_p]
     L.b200bo_last_kernel_ms.argtypes = [C.POINTER(C.c_float)]
+    philox_outs = [dp, i64p, dp, dp, i64p, dp]
+    L.b200bo_acq_argmin_topk_philox.argtypes = [C.POINTER(AcqSpec), C.c_uint64, dp, dp, C.c_int64, C.c_int64,
+                                                C.c_int, *philox_outs]
+    L.b200bo_acq_select_philox_dev.argtypes = [C.POINTER(AcqSpec), C.c_uint64, dp, dp, C.c_int64, C.c_int64,
+                                               C.c_int, C.c_void_p, C.c_void_p]
+    L.b200bo_philox_rows.argtypes = [C.c_int, C.c_uint64, dp, dp, C.c_int, i64p, C.c_int64, dp]
+    L.b200bo_gp_replicate.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.b200bo_multi_gpu_acq_argmin_topk.argtypes = [C.POINTER(AcqSpec), C.c_int, dp, C.c_int64, C.c_int, dp,
+                                                   i64p, dp, i64p]
+    L.b200bo_multi_gpu_acq_argmin_topk_philox.argtypes = [C.POINTER(AcqSpec), C.c_int, C.c_uint64, dp, dp,
+                                                          C.c_int64, C.c_int64, C.c_int, *philox_outs]
+    L.b200bo_multi_gpu_acq_eval.argtypes = [C.POINTER(AcqSpec), C.c_int, dp, C.c_int64, i64p, dp]
     _lib = L
     return L
 

@@ -7,7 +7,15 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
+
+#include <dlfcn.h>
+#include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include "fit_kernels.cuh"
 #include "predict_kernels.cuh"
@@ -37,6 +45,13 @@ static int set_err(int code, const char* fmt, ...) {
     } while (0)
 
 #define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+// NVTX ranges around the phases of the path (fit / lml / predict_acq / select / exchange): visible in any
+// NVTX-aware profiler, free otherwise (header-only NVTX3 resolves its injection library lazily).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ---------------------------------------------------------------------------------------
 // handle
@@ -90,6 +105,12 @@ struct b200bo_gp {
     DevBuf tc_linv;
     bool tc_valid = false;
     DevBuf cov_xc, cov_kst, cov_v, cov_c, cov_out, cov_mu;  // predict(return_cov=True) scratch
+    DevBuf sel_cta;         // per-CTA running selection lists of the fused kernels
+    DevBuf pbounds, prow;   // throughput mode: Philox bounds (lo, span) / regenerated winner rows
+    bool replica = false;   // predict-only copy made by b200bo_gp_replicate
+    // streamed host batches: copy / execute streams and the double-buffer events
+    cudaStream_t copy_stream = nullptr, exec_stream = nullptr;
+    cudaEvent_t chunk_up[2] = {nullptr, nullptr}, chunk_done[2] = {nullptr, nullptr};
     int precision = B200BO_PRECISION_FP64;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // fit-side work (set_data / fit / lml) of this handle is issued on this stream: the legacy default
@@ -198,9 +219,16 @@ extern "C" void b200bo_gp_destroy(b200bo_gp* gp) {
                       &gp->alphav, &gp->v1, &gp->v2, &gp->ls, &gp->xf, &gp->info, &gp->part,
                       &gp->pscratch, &gp->xc, &gp->out_acq, &gp->out_mu, &gp->out_sd, &gp->sel,
                       &gp->clamp, &gp->s_ksm, &gp->s_partial, &gp->s_mupart, &gp->s_unit, &gp->s_rb,
-                      &gp->tc_linv, &gp->cov_xc, &gp->cov_kst, &gp->cov_v, &gp->cov_c, &gp->cov_out, &gp->cov_mu};
+                      &gp->tc_linv, &gp->cov_xc, &gp->cov_kst, &gp->cov_v, &gp->cov_c, &gp->cov_out, &gp->cov_mu,
+                      &gp->sel_cta, &gp->pbounds, &gp->prow};
     for (DevBuf* b : bufs) b->release();
     if (gp->stream) cudaStreamDestroy(gp->stream);
+    if (gp->copy_stream) cudaStreamDestroy(gp->copy_stream);
+    if (gp->exec_stream) cudaStreamDestroy(gp->exec_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (gp->chunk_up[i]) cudaEventDestroy(gp->chunk_up[i]);
+        if (gp->chunk_done[i]) cudaEventDestroy(gp->chunk_done[i]);
+    }
     if (gp->ev0) cudaEventDestroy(gp->ev0);
     if (gp->ev1) cudaEventDestroy(gp->ev1);
     if (g_last_timed == gp) g_last_timed = nullptr;
@@ -260,6 +288,7 @@ extern "C" int b200bo_gp_set_data(b200bo_gp* gp, const double* X, const double* 
     CU(cudaSetDevice(gp->device));
     StreamScope scope(gp);
     gp->fitted = false;
+    gp->replica = false;
     gp->tc_valid = false;
     gp->n = n;
     gp->d = d;
@@ -473,6 +502,7 @@ extern "C" int b200bo_gp_fit(b200bo_gp* gp, const double* X, const double* y, in
     if ((rc = b200bo_gp_set_data(gp, X, y, n, d, normalize_y))) return rc;
     if ((rc = check_kernel(gp, kern))) return rc;
     StreamScope scope(gp);
+    NvtxRange nvtx_range("b200bo:fit");
     if (info) *info = 0;
     int finfo = 0;
     if ((rc = factorize(gp, kern, alpha, &finfo))) return rc;
@@ -496,6 +526,7 @@ extern "C" int b200bo_gp_fit(b200bo_gp* gp, const double* X, const double* y, in
 extern "C" int b200bo_gp_append(b200bo_gp* gp, const double* x_new, double y_new, int64_t* info) {
     if (!gp || !x_new) return set_err(B200BO_ERR_ARG, "NULL argument");
     if (!gp->fitted) return set_err(B200BO_ERR_STATE, "GP handle is not fitted");
+    if (gp->replica) return set_err(B200BO_ERR_STATE, "handle is a predict-only replica: append to the source and replicate again");
     if (gp->n >= gp->np) return set_err(B200BO_ERR_STATE, "no padding slack left (n == np): refit");
     CU(cudaSetDevice(gp->device));
     const int n = (int)gp->n, np = gp->np, d = gp->d;
@@ -565,6 +596,7 @@ extern "C" int b200bo_gp_lml(b200bo_gp* gp, const b200bo_kernel* kern, double al
     if ((rc = check_kernel(gp, kern))) return rc;
     CU(cudaSetDevice(gp->device));
     StreamScope scope(gp);
+    NvtxRange nvtx_range("b200bo:lml");
     gp->fitted = false;  // buffers are being overwritten
     gp->tc_valid = false;
     const int n = (int)gp->n, np = gp->np, d = gp->d;
@@ -622,6 +654,8 @@ extern "C" int b200bo_gp_get(b200bo_gp* gp, int what, double* out, int64_t len) 
     CU(cudaSetDevice(gp->device));
     const size_t n = gp->n, np = gp->np;
     const void* src = nullptr;
+    if (gp->replica && (what == B200BO_GET_L || what == B200BO_GET_K))
+        return set_err(B200BO_ERR_STATE, "a predict-only replica holds no K / L: read them from the source handle");
     switch (what) {
         case B200BO_GET_L: src = gp->L.p; break;
         case B200BO_GET_K: src = gp->K.p; break;
@@ -673,10 +707,13 @@ static int ensure_small(b200bo_gp* gp) {
 
 // Cost model (microseconds, measured orders of magnitude on B200) choosing between the tiled
 // persistent kernel and the small-batch path.  B200BO_SMALL_PATH=0/1 forces one of them.
-static bool use_small_path(long long m, int np_max, int n_gps, int sm_count) {
+// B200BO_PATH_STABLE: the decision is taken for a nominal batch of one pass (SMC rows) whatever m is,
+// so an optimiser's f(x) and its finite-difference stencil always run through the same kernels.
+static bool use_small_path(long long m, int np_max, int n_gps, int sm_count, int path) {
     const char* e = getenv("B200BO_SMALL_PATH");
     if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
     if (m <= 0) return false;
+    if (path == B200BO_PATH_STABLE) m = SMC;
     const double x = (np_max / 4096.0) * (np_max / 4096.0);
     const double passes = (double)((m + SMC - 1) / SMC);
     const double tiles = (double)((m + PBN - 1) / PBN);
@@ -716,6 +753,8 @@ static int check_spec(const b200bo_acq* spec) {
         return set_err(B200BO_ERR_ARG, "n_gps=%d out of range [1,%d]", spec->n_gps, B200BO_MAX_GPS);
     if (spec->kind < B200BO_ACQ_UCB || spec->kind > B200BO_ACQ_NONE)
         return set_err(B200BO_ERR_ARG, "unknown acquisition kind %d", spec->kind);
+    if (spec->path != B200BO_PATH_AUTO && spec->path != B200BO_PATH_STABLE)
+        return set_err(B200BO_ERR_ARG, "unknown path policy %d", spec->path);
     for (int g = 0; g < spec->n_gps; ++g) {
         const b200bo_gp* gp = spec->gps[g];
         if (!gp) return set_err(B200BO_ERR_ARG, "gps[%d] is NULL", g);
@@ -729,22 +768,35 @@ static int check_spec(const b200bo_acq* spec) {
     return B200BO_OK;
 }
 
-extern "C" int b200bo_acq_eval_dev(const b200bo_acq* spec, const double* d_Xc, int64_t m,
-                                   double* d_acq_neg, double* d_mu, double* d_sd, int k, void* d_sel,
-                                   int64_t index_base, void* stream_) {
+// Where a launch's candidates come from: a device matrix (parity mode: the reference's host MT19937 stream,
+// uploaded) or the in-kernel Philox generator (throughput mode).
+struct CandSrc {
+    const double* d_Xc = nullptr;
+    bool philox = false;
+    uint64_t seed = 0;
+    const double* lo = nullptr;  // host, d entries
+    const double* hi = nullptr;
+};
+
+// resume != 0: the per-CTA selection lists of the previous launch on this handle are continued instead of
+// re-initialised (chunked batches: one merge after the last chunk); finish == 0 skips the merge.
+struct SelMode {
+    int resume = 0;
+    int finish = 1;
+};
+
+static int eval_core(const b200bo_acq* spec, const CandSrc& src, int64_t m, double* d_acq_neg, double* d_mu,
+                     double* d_sd, int k, void* d_sel, int64_t index_base, cudaStream_t stream,
+                     SelMode sm = SelMode()) {
     int rc;
     if ((rc = check_spec(spec))) return rc;
-    if (m < 0 || (m > 0 && !d_Xc)) return set_err(B200BO_ERR_ARG, "bad candidates");
+    if (m < 0 || (m > 0 && !src.philox && !src.d_Xc)) return set_err(B200BO_ERR_ARG, "bad candidates");
+    if (src.philox && (!src.lo || !src.hi)) return set_err(B200BO_ERR_ARG, "Philox mode needs lo/hi");
     if (k < 0 || k > B200BO_MAX_TOPK) return set_err(B200BO_ERR_ARG, "k=%d out of range", k);
     if (k > 0 && !d_sel) return set_err(B200BO_ERR_ARG, "d_sel is NULL");
     b200bo_gp* g0 = spec->gps[0];
     CU(cudaSetDevice(g0->device));
-    cudaStream_t stream = (cudaStream_t)stream_;
-    double* acq_buf = d_acq_neg;
-    if (k > 0 && !acq_buf) {
-        if ((rc = g0->out_acq.reserve(sizeof(double) * (size_t)(m > 0 ? m : 1)))) return rc;
-        acq_buf = g0->out_acq.as<double>();
-    }
+    NvtxRange nvtx_range("b200bo:predict_acq");
     PredictParams P;
     memset(&P, 0, sizeof(P));
     int np_max = 0;
@@ -774,17 +826,38 @@ extern "C" int b200bo_acq_eval_dev(const b200bo_acq* spec, const double* d_Xc, i
     P.kappa = spec->kappa;
     P.xi = spec->xi;
     P.y_max = spec->y_max;
-    P.Xc = d_Xc;
+    P.Xc = src.philox ? nullptr : src.d_Xc;
+    P.index_base = index_base;
+    if (src.philox) {
+        double pb[2 * B200BO_MAX_DIM];
+        for (int j = 0; j < P.d; ++j) {
+            if (!(src.lo[j] <= src.hi[j])) return set_err(B200BO_ERR_ARG, "Philox bounds: lo > hi in column %d", j);
+            pb[j] = src.lo[j];
+            pb[P.d + j] = src.hi[j] - src.lo[j];
+        }
+        if ((rc = g0->pbounds.reserve(sizeof(double) * 2 * B200BO_MAX_DIM))) return rc;
+        CU(cudaMemcpyAsync(g0->pbounds.p, pb, sizeof(double) * 2 * P.d, cudaMemcpyHostToDevice, stream));
+        P.pbounds = g0->pbounds.as<double>();
+        P.seed = src.seed;
+    }
     P.m = m;
-    P.acq_out = acq_buf;
+    P.acq_out = d_acq_neg;
     P.mu_out = d_mu;
     P.sd_out = d_sd;
     if ((rc = g0->clamp.reserve(sizeof(unsigned long long)))) return rc;
     P.clamp_count = g0->clamp.as<unsigned long long>();
-    CU(cudaMemsetAsync(g0->clamp.p, 0, sizeof(unsigned long long), stream));
+    if (!sm.resume) CU(cudaMemsetAsync(g0->clamp.p, 0, sizeof(unsigned long long), stream));
     const long long ntiles = (m + PBN - 1) / PBN;
     int grid = (int)(ntiles < g0->sm_count ? ntiles : g0->sm_count);
-    if (grid > 0 && use_small_path(m, np_max, spec->n_gps, g0->sm_count)) {
+    if (sm.resume || !sm.finish) grid = g0->sm_count;  // chunked batches keep one list per SM across launches
+    const bool small = grid > 0 && !sm.resume && sm.finish &&
+                       use_small_path(m, np_max, spec->n_gps, g0->sm_count, spec->path);
+    bool fused_sel = false;
+    if (small) {
+        if (k > 0 && !P.acq_out) {  // the small path selects from the materialised values
+            if ((rc = g0->out_acq.reserve(sizeof(double) * (size_t)(m > 0 ? m : 1)))) return rc;
+            P.acq_out = g0->out_acq.as<double>();
+        }
         SmallParams S;
         memset(&S, 0, sizeof(S));
         S.P = P;
@@ -815,6 +888,13 @@ extern "C" int b200bo_acq_eval_dev(const b200bo_acq* spec, const double* d_Xc, i
         CU(cudaEventRecord(g0->ev1, stream));
         g_last_timed = g0;
     } else if (grid > 0) {
+        if (k > 0) {  // selection fused into the epilogue: no acq[M] needed
+            if ((rc = g0->sel_cta.reserve(sizeof(SelList) * (size_t)g0->sm_count))) return rc;
+            P.sel_cta = g0->sel_cta.as<SelList>();
+            P.sel_k = k;
+            P.sel_resume = sm.resume;
+            fused_sel = true;
+        }
         P.scratch_stride = (long long)np_max * PBN;
         if ((rc = g0->pscratch.reserve(sizeof(double) * (size_t)P.scratch_stride * g0->sm_count))) return rc;
         P.scratch = g0->pscratch.as<double>();
@@ -855,12 +935,41 @@ extern "C" int b200bo_acq_eval_dev(const b200bo_acq* spec, const double* d_Xc, i
         CU(cudaEventRecord(g0->ev1, stream));
         g_last_timed = g0;
     }
-    if (k > 0) {
-        select_kernel<<<1, 1024, 0, stream>>>(acq_buf, m, k, reinterpret_cast<SelRecord*>(d_sel), index_base);
+    if (k > 0 && sm.finish) {
+        NvtxRange nvtx_sel("b200bo:select");
+        if (fused_sel) {
+            merge_sel_kernel<<<1, 256, 0, stream>>>(g0->sel_cta.as<SelList>(), grid, k,
+                                                    reinterpret_cast<SelRecord*>(d_sel));
+        } else if (m > 0) {
+            select_kernel<<<1, 1024, 0, stream>>>(P.acq_out, m, k, reinterpret_cast<SelRecord*>(d_sel), index_base);
+        } else {
+            CU(cudaMemsetAsync(d_sel, 0xFF, sizeof(SelRecord) * (k + 1), stream));  // empty: index -1, value NaN
+        }
         LAUNCHED();
         CU(cudaGetLastError());
     }
     return B200BO_OK;
+}
+
+extern "C" int b200bo_acq_eval_dev(const b200bo_acq* spec, const double* d_Xc, int64_t m,
+                                   double* d_acq_neg, double* d_mu, double* d_sd, int k, void* d_sel,
+                                   int64_t index_base, void* stream_) {
+    CandSrc src;
+    src.d_Xc = d_Xc;
+    return eval_core(spec, src, m, d_acq_neg, d_mu, d_sd, k, d_sel, index_base, (cudaStream_t)stream_);
+}
+
+extern "C" int b200bo_acq_select_philox_dev(const b200bo_acq* spec, uint64_t seed, const double* lo,
+                                            const double* hi, int64_t m, int64_t index_base, int k, void* d_sel,
+                                            void* stream_) {
+    if (k <= 0) return set_err(B200BO_ERR_ARG, "k must be > 0");
+    if (m <= 0) return set_err(B200BO_ERR_ARG, "m must be > 0");
+    CandSrc src;
+    src.philox = true;
+    src.seed = seed;
+    src.lo = lo;
+    src.hi = hi;
+    return eval_core(spec, src, m, nullptr, nullptr, nullptr, k, d_sel, index_base, (cudaStream_t)stream_);
 }
 
 extern "C" int b200bo_last_kernel_ms(float* ms) {
@@ -872,24 +981,85 @@ extern "C" int b200bo_last_kernel_ms(float* ms) {
     return B200BO_OK;
 }
 
-// host-buffer front end shared by predict / acq_eval / argmin_topk
+// Host-buffer front end shared by predict / acq_eval / argmin_topk.  Large selection-only batches are
+// streamed: the candidate matrix goes up in chunks of a whole number of tiles per SM on a copy stream while
+// the previous chunk is evaluated (double-buffered device chunks), the per-CTA selection lists carry over
+// from launch to launch and are merged once - the H2D copy disappears behind the kernel.
+constexpr long long kChunkTilesPerSm = 8;
+
+static int ensure_copy_stream(b200bo_gp* g0) {
+    if (!g0->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&g0->copy_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&g0->exec_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&g0->chunk_up[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&g0->chunk_done[i], cudaEventDisableTiming));
+        }
+    }
+    return B200BO_OK;
+}
+
+static int run_host_chunked(const b200bo_acq* spec, const double* Xc, int64_t m, int k, SelRecord* sel_host) {
+    b200bo_gp* g0 = spec->gps[0];
+    int rc;
+    if ((rc = ensure_copy_stream(g0))) return rc;
+    const int d = g0->d;
+    const long long chunk = kChunkTilesPerSm * PBN * g0->sm_count;
+    if ((rc = g0->xc.reserve(sizeof(double) * (size_t)2 * chunk * d))) return rc;
+    if ((rc = g0->sel.reserve(sizeof(SelRecord) * (B200BO_MAX_TOPK + 1)))) return rc;
+    double* buf[2] = {g0->xc.as<double>(), g0->xc.as<double>() + (size_t)chunk * d};
+    int i = 0;
+    for (long long c0 = 0; c0 < m; c0 += chunk, ++i) {
+        const long long mc = (m - c0) < chunk ? (m - c0) : chunk;
+        const int b = i & 1;
+        if (i >= 2) CU(cudaStreamWaitEvent(g0->copy_stream, g0->chunk_done[b], 0));  // buffer b consumed
+        CU(cudaMemcpyAsync(buf[b], Xc + (size_t)c0 * d, sizeof(double) * (size_t)mc * d, cudaMemcpyHostToDevice,
+                           g0->copy_stream));
+        CU(cudaEventRecord(g0->chunk_up[b], g0->copy_stream));
+        CU(cudaStreamWaitEvent(g0->exec_stream, g0->chunk_up[b], 0));
+        CandSrc src;
+        src.d_Xc = buf[b];
+        SelMode sm;
+        sm.resume = i > 0;
+        sm.finish = (c0 + chunk >= m);
+        if ((rc = eval_core(spec, src, mc, nullptr, nullptr, nullptr, k, g0->sel.p, c0, g0->exec_stream, sm)))
+            return rc;
+        CU(cudaEventRecord(g0->chunk_done[b], g0->exec_stream));
+    }
+    CU(cudaStreamSynchronize(g0->exec_stream));
+    CU(cudaMemcpy(sel_host, g0->sel.p, sizeof(SelRecord) * (k + 1), cudaMemcpyDeviceToHost));
+    return B200BO_OK;
+}
+
 static int run_host(const b200bo_acq* spec, const double* Xc, int64_t m, double* acq_neg, double* mu,
-                    double* sd, int k, SelRecord* sel_host, int64_t* n_clamped) {
+                    double* sd, int k, SelRecord* sel_host, int64_t* n_clamped, int64_t index_base = 0) {
     int rc;
     if ((rc = check_spec(spec))) return rc;
     if (m < 0 || (m > 0 && !Xc)) return set_err(B200BO_ERR_ARG, "bad candidates");
     b200bo_gp* g0 = spec->gps[0];
     CU(cudaSetDevice(g0->device));
+    {
+        int np_max = 0;
+        for (int g = 0; g < spec->n_gps; ++g) np_max = spec->gps[g]->np > np_max ? spec->gps[g]->np : np_max;
+        const long long chunk = kChunkTilesPerSm * PBN * g0->sm_count;
+        const char* e = getenv("B200BO_CHUNKED");
+        const bool allow = !(e && e[0] == '0');
+        if (allow && k > 0 && sel_host && !acq_neg && !mu && !sd && !n_clamped && index_base == 0 && m >= 2 * chunk &&
+            !use_small_path(m, np_max, spec->n_gps, g0->sm_count, spec->path))
+            return run_host_chunked(spec, Xc, m, k, sel_host);
+    }
     const size_t mm = (size_t)(m > 0 ? m : 1);
     if ((rc = g0->xc.reserve(sizeof(double) * mm * g0->d))) return rc;
-    if ((rc = g0->out_acq.reserve(sizeof(double) * mm))) return rc;
+    if (acq_neg && (rc = g0->out_acq.reserve(sizeof(double) * mm))) return rc;
     if (mu && (rc = g0->out_mu.reserve(sizeof(double) * mm))) return rc;
     if (sd && (rc = g0->out_sd.reserve(sizeof(double) * mm))) return rc;
     if ((rc = g0->sel.reserve(sizeof(SelRecord) * (B200BO_MAX_TOPK + 1)))) return rc;
     if (m > 0) CU(cudaMemcpy(g0->xc.p, Xc, sizeof(double) * (size_t)m * g0->d, cudaMemcpyHostToDevice));
-    if ((rc = b200bo_acq_eval_dev(spec, g0->xc.as<double>(), m, g0->out_acq.as<double>(),
-                                  mu ? g0->out_mu.as<double>() : nullptr,
-                                  sd ? g0->out_sd.as<double>() : nullptr, k, g0->sel.p, 0, nullptr)))
+    CandSrc src;
+    src.d_Xc = g0->xc.as<double>();
+    if ((rc = eval_core(spec, src, m, acq_neg ? g0->out_acq.as<double>() : nullptr,
+                        mu ? g0->out_mu.as<double>() : nullptr, sd ? g0->out_sd.as<double>() : nullptr, k,
+                        g0->sel.p, index_base, nullptr)))
         return rc;
     CU(cudaDeviceSynchronize());
     if (m > 0) {
@@ -923,7 +1093,8 @@ extern "C" int b200bo_gp_predict_cov(b200bo_gp* gp, const double* Xc, int64_t m,
     if (!gp->fitted) return set_err(B200BO_ERR_STATE, "GP handle is not fitted");
     if (m <= 0 || m > 16384) return set_err(B200BO_ERR_ARG, "return_cov supports 1 <= m <= 16384 (m=%lld)", (long long)m);
     CU(cudaSetDevice(gp->device));
-    const int n = (int)gp->n, np = gp->np, d = gp->d, mi = (int)m, mp = round_up(m, 64);
+    StreamScope scope(nullptr);  // legacy default stream
+    const int n = (int)gp->n, np = gp->np, d = gp->d, mi = (int)m, mp = round_up(m, 128);
     int rc;
     if ((rc = gp->cov_xc.reserve(sizeof(double) * (size_t)mp * d))) return rc;
     if ((rc = gp->cov_kst.reserve(sizeof(double) * (size_t)np * mp))) return rc;
@@ -972,6 +1143,16 @@ extern "C" int b200bo_acq_eval(const b200bo_acq* spec, const double* Xc, int64_t
     return run_host(spec, Xc, m, acq_neg, nullptr, nullptr, 0, nullptr, nullptr);
 }
 
+static void unpack_records(const SelRecord* sel, int k, double* best_val, int64_t* best_idx, double* topk_val,
+                           int64_t* topk_idx) {
+    if (best_val) *best_val = sel[0].value;
+    if (best_idx) *best_idx = sel[0].index;
+    for (int i = 0; i < k; ++i) {
+        if (topk_val) topk_val[i] = sel[1 + i].value;
+        if (topk_idx) topk_idx[i] = sel[1 + i].index;
+    }
+}
+
 extern "C" int b200bo_acq_argmin_topk(const b200bo_acq* spec, const double* Xc, int64_t m, int k,
                                       double* best_val, int64_t* best_idx, double* topk_val,
                                       int64_t* topk_idx, double* acq_neg) {
@@ -982,11 +1163,369 @@ extern "C" int b200bo_acq_argmin_topk(const b200bo_acq* spec, const double* Xc, 
     // k = 0 still needs the argmin record: run the selection with one round
     int rc = run_host(spec, Xc, m, acq_neg, nullptr, nullptr, k > 0 ? k : 1, sel, nullptr);
     if (rc) return rc;
-    if (best_val) *best_val = sel[0].value;
-    if (best_idx) *best_idx = sel[0].index;
-    for (int i = 0; i < k; ++i) {
-        if (topk_val) topk_val[i] = sel[1 + i].value;
-        if (topk_idx) topk_idx[i] = sel[1 + i].index;
+    unpack_records(sel, k, best_val, best_idx, topk_val, topk_idx);
+    return B200BO_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// throughput mode (device Philox candidates)
+// ---------------------------------------------------------------------------------------
+// coordinates of the records' rows, regenerated on the device of g0 into host memory (k+1 rows)
+static int philox_rows_of_records(b200bo_gp* g0, uint64_t seed, const SelRecord* d_rec, int nrec, int d,
+                                  double* rows_host, cudaStream_t stream) {
+    int rc;
+    if ((rc = g0->prow.reserve(sizeof(double) * (size_t)(B200BO_MAX_TOPK + 1) * B200BO_MAX_DIM))) return rc;
+    philox_rows_kernel<<<nrec, 64, 0, stream>>>(seed, g0->pbounds.as<double>(), d, d_rec, nrec, g0->prow.as<double>());
+    LAUNCHED();
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(rows_host, g0->prow.p, sizeof(double) * (size_t)nrec * d, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    return B200BO_OK;
+}
+
+extern "C" int b200bo_acq_argmin_topk_philox(const b200bo_acq* spec, uint64_t seed, const double* lo,
+                                             const double* hi, int64_t m, int64_t index_base, int k,
+                                             double* best_val, int64_t* best_idx, double* best_x, double* topk_val,
+                                             int64_t* topk_idx, double* topk_x) {
+    if (k < 0 || k > B200BO_MAX_TOPK) return set_err(B200BO_ERR_ARG, "k=%d out of range", k);
+    if (m <= 0) return set_err(B200BO_ERR_ARG, "m must be > 0");
+    int rc;
+    if ((rc = check_spec(spec))) return rc;
+    if (spec->kind == B200BO_ACQ_NONE) return set_err(B200BO_ERR_ARG, "kind NONE has no acquisition");
+    b200bo_gp* g0 = spec->gps[0];
+    CU(cudaSetDevice(g0->device));
+    if ((rc = g0->sel.reserve(sizeof(SelRecord) * (B200BO_MAX_TOPK + 1)))) return rc;
+    const int kk = k > 0 ? k : 1;
+    if ((rc = b200bo_acq_select_philox_dev(spec, seed, lo, hi, m, index_base, kk, g0->sel.p, nullptr))) return rc;
+    SelRecord sel[B200BO_MAX_TOPK + 1];
+    CU(cudaMemcpy(sel, g0->sel.p, sizeof(SelRecord) * (kk + 1), cudaMemcpyDeviceToHost));
+    unpack_records(sel, k, best_val, best_idx, topk_val, topk_idx);
+    if (best_x || (topk_x && k > 0)) {
+        std::vector<double> rows((size_t)(kk + 1) * g0->d);
+        if ((rc = philox_rows_of_records(g0, seed, g0->sel.as<SelRecord>(), kk + 1, g0->d, rows.data(), nullptr)))
+            return rc;
+        if (best_x) memcpy(best_x, rows.data(), sizeof(double) * g0->d);
+        if (topk_x && k > 0) memcpy(topk_x, rows.data() + g0->d, sizeof(double) * (size_t)k * g0->d);
     }
     return B200BO_OK;
+}
+
+extern "C" int b200bo_philox_rows(int device, uint64_t seed, const double* lo, const double* hi, int d,
+                                  const int64_t* idx, int64_t n_idx, double* out) {
+    if (!lo || !hi || !idx || !out) return set_err(B200BO_ERR_ARG, "NULL argument");
+    if (d <= 0 || d > B200BO_MAX_DIM || n_idx < 0) return set_err(B200BO_ERR_ARG, "bad shape");
+    if (n_idx == 0) return B200BO_OK;
+    CU(cudaSetDevice(device));
+    std::vector<SelRecord> rec((size_t)n_idx);
+    std::vector<double> pb(2 * d);
+    for (int j = 0; j < d; ++j) {
+        pb[j] = lo[j];
+        pb[d + j] = hi[j] - lo[j];
+    }
+    for (int64_t i = 0; i < n_idx; ++i) {
+        rec[i].value = 0.0;
+        rec[i].index = idx[i];
+    }
+    SelRecord* d_rec = nullptr;
+    double *d_pb = nullptr, *d_out = nullptr;
+    CU(cudaMalloc(&d_rec, sizeof(SelRecord) * n_idx));
+    CU(cudaMalloc(&d_pb, sizeof(double) * 2 * d));
+    CU(cudaMalloc(&d_out, sizeof(double) * n_idx * d));
+    CU(cudaMemcpy(d_rec, rec.data(), sizeof(SelRecord) * n_idx, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_pb, pb.data(), sizeof(double) * 2 * d, cudaMemcpyHostToDevice));
+    philox_rows_kernel<<<(unsigned)n_idx, 64>>>(seed, d_pb, d, d_rec, (int)n_idx, d_out);
+    LAUNCHED();
+    cudaError_t e = cudaMemcpy(out, d_out, sizeof(double) * n_idx * d, cudaMemcpyDeviceToHost);
+    cudaFree(d_rec);
+    cudaFree(d_pb);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return set_err(B200BO_ERR_CUDA, "philox_rows: %s", cudaGetErrorString(e));
+    return B200BO_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// multi-GPU (one process, G devices of one box): SURVEY.md 8e
+// ---------------------------------------------------------------------------------------
+extern "C" int b200bo_gp_replicate(const b200bo_gp* src, int device, b200bo_gp** out) {
+    if (!src || !out) return set_err(B200BO_ERR_ARG, "NULL argument");
+    if (!src->fitted) return set_err(B200BO_ERR_STATE, "source GP handle is not fitted");
+    b200bo_gp* dst = nullptr;
+    int rc;
+    if ((rc = b200bo_gp_create(&dst, device))) return rc;
+    NvtxRange nvtx_range("b200bo:replicate");
+    dst->n = src->n;
+    dst->np = src->np;
+    dst->d = src->d;
+    dst->family = src->family;
+    dst->nu = src->nu;
+    dst->constv = src->constv;
+    dst->jitter = src->jitter;
+    dst->y_mean = src->y_mean;
+    dst->y_std = src->y_std;
+    dst->normalize = src->normalize;
+    dst->xform = src->xform;
+    dst->precision = src->precision;
+    dst->replica = true;
+    const size_t np = src->np, d = src->d;
+    struct Item {
+        DevBuf* to;
+        const DevBuf* from;
+        size_t bytes;
+    } items[] = {
+        {&dst->Xs, &src->Xs, sizeof(double) * np * d},        {&dst->WT, &src->WT, sizeof(double) * np * np},
+        {&dst->W, &src->W, sizeof(double) * np * np},          {&dst->alphav, &src->alphav, sizeof(double) * np},
+        {&dst->ls, &src->ls, sizeof(double) * B200BO_MAX_DIM}, {&dst->xf, &src->xf, sizeof(int) * B200BO_MAX_DIM},
+    };
+    for (const Item& it : items) {
+        if ((rc = it.to->reserve(it.bytes))) {
+            b200bo_gp_destroy(dst);
+            return rc;
+        }
+        cudaError_t e = cudaMemcpyPeer(it.to->p, device, it.from->p, src->device, it.bytes);
+        if (e != cudaSuccess) {
+            b200bo_gp_destroy(dst);
+            return set_err(B200BO_ERR_CUDA, "cudaMemcpyPeer %d -> %d failed: %s", src->device, device,
+                           cudaGetErrorString(e));
+        }
+    }
+    CU(cudaSetDevice(src->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaSetDevice(device));
+    CU(cudaDeviceSynchronize());
+    dst->fitted = true;
+    *out = dst;
+    return B200BO_OK;
+}
+
+// NCCL is reached through dlopen so that the library has no link-time dependency on it: inside a Python
+// process that already imported torch this binds to torch's bundled libnccl.so.2, otherwise to the system one.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static std::mutex g_multi_mu;
+
+static int load_nccl() {
+    if (g_nccl.handle) return B200BO_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return set_err(B200BO_ERR_CUDA, "cannot load libnccl.so.2: %s", dlerror());
+    g_nccl.CommInitAll = (decltype(g_nccl.CommInitAll))dlsym(h, "ncclCommInitAll");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
+    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(h, "ncclGroupEnd");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.CommInitAll || !g_nccl.AllGather || !g_nccl.GroupStart || !g_nccl.GroupEnd || !g_nccl.GetErrorString)
+        return set_err(B200BO_ERR_CUDA, "libnccl.so.2 lacks a required symbol");
+    g_nccl.handle = h;
+    return B200BO_OK;
+}
+
+#define NC(call)                                                                                    \
+    do {                                                                                            \
+        ncclResult_t r__ = (call);                                                                  \
+        if (r__ != ncclSuccess)                                                                     \
+            return set_err(B200BO_ERR_CUDA, "%s failed: %s", #call, g_nccl.GetErrorString(r__));    \
+    } while (0)
+
+constexpr int kMaxDev = 16;
+struct MultiCtx {
+    int n = 0;
+    int dev[kMaxDev];
+    ncclComm_t comm[kMaxDev];
+    cudaStream_t stream[kMaxDev];
+    SelRecord* sel[kMaxDev];     // (MAX_TOPK+1) local records on device g
+    SelRecord* gather[kMaxDev];  // n * (MAX_TOPK+1) records on device g
+    SelRecord* merged = nullptr; // (MAX_TOPK+1) on device 0
+};
+static std::map<std::vector<int>, MultiCtx*> g_multi;
+
+// communicators + exchange buffers for a device list (created on first use, kept for the process lifetime)
+static int multi_ctx(const b200bo_acq* specs, int n_dev, MultiCtx** out) {
+    if (!specs || n_dev < 1 || n_dev > kMaxDev) return set_err(B200BO_ERR_ARG, "n_dev=%d out of range [1,%d]", n_dev, kMaxDev);
+    std::vector<int> devs;
+    int rc;
+    for (int g = 0; g < n_dev; ++g) {
+        if ((rc = check_spec(&specs[g]))) return rc;
+        if (specs[g].n_gps != specs[0].n_gps || specs[g].kind != specs[0].kind)
+            return set_err(B200BO_ERR_ARG, "specs[%d] describes a different acquisition", g);
+        const int dv = specs[g].gps[0]->device;
+        for (int q : devs)
+            if (q == dv) return set_err(B200BO_ERR_ARG, "device %d appears twice", dv);
+        devs.push_back(dv);
+    }
+    auto it = g_multi.find(devs);
+    if (it != g_multi.end()) {
+        *out = it->second;
+        return B200BO_OK;
+    }
+    if ((rc = load_nccl())) return rc;
+    MultiCtx* c = new MultiCtx();
+    c->n = n_dev;
+    for (int g = 0; g < n_dev; ++g) c->dev[g] = devs[g];
+    NC(g_nccl.CommInitAll(c->comm, n_dev, c->dev));
+    for (int g = 0; g < n_dev; ++g) {
+        CU(cudaSetDevice(c->dev[g]));
+        CU(cudaStreamCreateWithFlags(&c->stream[g], cudaStreamNonBlocking));
+        CU(cudaMalloc(&c->sel[g], sizeof(SelRecord) * (B200BO_MAX_TOPK + 1)));
+        CU(cudaMalloc(&c->gather[g], sizeof(SelRecord) * (B200BO_MAX_TOPK + 1) * n_dev));
+    }
+    CU(cudaSetDevice(c->dev[0]));
+    CU(cudaMalloc(&c->merged, sizeof(SelRecord) * (B200BO_MAX_TOPK + 1)));
+    g_multi[devs] = c;
+    *out = c;
+    return B200BO_OK;
+}
+
+static void shard_range(int64_t m, int g, int n, int64_t* s, int64_t* e) {
+    const int64_t base = m / n, rem = m % n;
+    *s = g * base + (g < rem ? g : rem);
+    *e = *s + base + (g < rem ? 1 : 0);
+}
+
+// run fn(g) on one host thread per device; the first failing rc and its message come back to the caller
+template <typename F>
+static int per_device(int n_dev, F fn) {
+    std::vector<int> rcs(n_dev, 0);
+    std::vector<std::string> msgs(n_dev);
+    std::vector<std::thread> th;
+    for (int g = 0; g < n_dev; ++g)
+        th.emplace_back([&, g]() {
+            rcs[g] = fn(g);
+            if (rcs[g]) msgs[g] = g_err;
+        });
+    for (auto& t : th) t.join();
+    for (int g = 0; g < n_dev; ++g)
+        if (rcs[g]) return set_err(rcs[g], "device slot %d: %s", g, msgs[g].c_str());
+    return B200BO_OK;
+}
+
+// the ONE exchange step + merge; the (k+1) merged records land in sel_host
+static int multi_exchange(MultiCtx* c, int k, SelRecord* sel_host) {
+    NvtxRange nvtx_range("b200bo:exchange");
+    const size_t bytes = sizeof(SelRecord) * (k + 1);
+    NC(g_nccl.GroupStart());
+    for (int g = 0; g < c->n; ++g)
+        NC(g_nccl.AllGather(c->sel[g], c->gather[g], bytes, ncclInt8, c->comm[g], c->stream[g]));
+    NC(g_nccl.GroupEnd());
+    CU(cudaSetDevice(c->dev[0]));
+    merge_records_kernel<<<1, 32, 0, c->stream[0]>>>(c->gather[0], c->n, k, c->merged);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(sel_host, c->merged, bytes, cudaMemcpyDeviceToHost, c->stream[0]));
+    for (int g = 0; g < c->n; ++g) {
+        CU(cudaSetDevice(c->dev[g]));
+        CU(cudaStreamSynchronize(c->stream[g]));
+    }
+    return B200BO_OK;
+}
+
+extern "C" int b200bo_multi_gpu_acq_argmin_topk(const b200bo_acq* specs, int n_dev, const double* Xc, int64_t m,
+                                                int k, double* best_val, int64_t* best_idx, double* topk_val,
+                                                int64_t* topk_idx) {
+    if (k < 0 || k > B200BO_MAX_TOPK) return set_err(B200BO_ERR_ARG, "k=%d out of range", k);
+    if (m <= 0 || !Xc) return set_err(B200BO_ERR_ARG, "bad candidates");
+    std::lock_guard<std::mutex> lock(g_multi_mu);
+    MultiCtx* c = nullptr;
+    int rc;
+    if ((rc = multi_ctx(specs, n_dev, &c))) return rc;
+    if (specs[0].kind == B200BO_ACQ_NONE) return set_err(B200BO_ERR_ARG, "kind NONE has no acquisition");
+    const int kk = k > 0 ? k : 1;
+    const int d = specs[0].gps[0]->d;
+    rc = per_device(n_dev, [&](int g) -> int {
+        int64_t s, e;
+        shard_range(m, g, n_dev, &s, &e);
+        b200bo_gp* g0 = specs[g].gps[0];
+        CU(cudaSetDevice(g0->device));
+        int r;
+        const int64_t mg = e - s;
+        if ((r = g0->xc.reserve(sizeof(double) * (size_t)(mg > 0 ? mg : 1) * d))) return r;
+        if (mg > 0)
+            CU(cudaMemcpyAsync(g0->xc.p, Xc + (size_t)s * d, sizeof(double) * (size_t)mg * d, cudaMemcpyHostToDevice,
+                               c->stream[g]));
+        CandSrc src;
+        src.d_Xc = g0->xc.as<double>();
+        return eval_core(&specs[g], src, mg, nullptr, nullptr, nullptr, kk, c->sel[g], s, c->stream[g]);
+    });
+    if (rc) return rc;
+    SelRecord sel[B200BO_MAX_TOPK + 1];
+    if ((rc = multi_exchange(c, kk, sel))) return rc;
+    unpack_records(sel, k, best_val, best_idx, topk_val, topk_idx);
+    return B200BO_OK;
+}
+
+extern "C" int b200bo_multi_gpu_acq_argmin_topk_philox(const b200bo_acq* specs, int n_dev, uint64_t seed,
+                                                       const double* lo, const double* hi, int64_t m,
+                                                       int64_t index_base, int k, double* best_val,
+                                                       int64_t* best_idx, double* best_x, double* topk_val,
+                                                       int64_t* topk_idx, double* topk_x) {
+    if (k < 0 || k > B200BO_MAX_TOPK) return set_err(B200BO_ERR_ARG, "k=%d out of range", k);
+    if (m <= 0) return set_err(B200BO_ERR_ARG, "m must be > 0");
+    std::lock_guard<std::mutex> lock(g_multi_mu);
+    MultiCtx* c = nullptr;
+    int rc;
+    if ((rc = multi_ctx(specs, n_dev, &c))) return rc;
+    if (specs[0].kind == B200BO_ACQ_NONE) return set_err(B200BO_ERR_ARG, "kind NONE has no acquisition");
+    const int kk = k > 0 ? k : 1;
+    rc = per_device(n_dev, [&](int g) -> int {
+        int64_t s, e;
+        shard_range(m, g, n_dev, &s, &e);
+        CU(cudaSetDevice(specs[g].gps[0]->device));
+        if (e == s) {
+            CU(cudaMemsetAsync(c->sel[g], 0xFF, sizeof(SelRecord) * (kk + 1), c->stream[g]));
+            return B200BO_OK;
+        }
+        CandSrc src;
+        src.philox = true;
+        src.seed = seed;
+        src.lo = lo;
+        src.hi = hi;
+        return eval_core(&specs[g], src, e - s, nullptr, nullptr, nullptr, kk, c->sel[g], index_base + s, c->stream[g]);
+    });
+    if (rc) return rc;
+    SelRecord sel[B200BO_MAX_TOPK + 1];
+    if ((rc = multi_exchange(c, kk, sel))) return rc;
+    unpack_records(sel, k, best_val, best_idx, topk_val, topk_idx);
+    if (best_x || (topk_x && k > 0)) {
+        b200bo_gp* g0 = specs[0].gps[0];
+        CU(cudaSetDevice(g0->device));
+        std::vector<double> rows((size_t)(kk + 1) * g0->d);
+        if ((rc = philox_rows_of_records(g0, seed, c->merged, kk + 1, g0->d, rows.data(), c->stream[0]))) return rc;
+        if (best_x) memcpy(best_x, rows.data(), sizeof(double) * g0->d);
+        if (topk_x && k > 0) memcpy(topk_x, rows.data() + g0->d, sizeof(double) * (size_t)k * g0->d);
+    }
+    return B200BO_OK;
+}
+
+extern "C" int b200bo_multi_gpu_acq_eval(const b200bo_acq* specs, int n_dev, const double* Xc, int64_t m,
+                                         const int64_t* offsets, double* acq_neg) {
+    if (m < 0 || (m > 0 && (!Xc || !acq_neg))) return set_err(B200BO_ERR_ARG, "bad candidates");
+    if (!specs || n_dev < 1 || n_dev > kMaxDev) return set_err(B200BO_ERR_ARG, "n_dev=%d out of range", n_dev);
+    int rc;
+    for (int g = 0; g < n_dev; ++g) {
+        if ((rc = check_spec(&specs[g]))) return rc;
+        if (specs[g].kind == B200BO_ACQ_NONE) return set_err(B200BO_ERR_ARG, "kind NONE has no acquisition");
+    }
+    if (offsets) {
+        if (offsets[0] != 0 || offsets[n_dev] != m) return set_err(B200BO_ERR_ARG, "offsets must span [0, m]");
+        for (int g = 0; g < n_dev; ++g)
+            if (offsets[g + 1] < offsets[g]) return set_err(B200BO_ERR_ARG, "offsets must be non-decreasing");
+    }
+    const int d = specs[0].gps[0]->d;
+    return per_device(n_dev, [&](int g) -> int {
+        int64_t s, e;
+        if (offsets) {
+            s = offsets[g];
+            e = offsets[g + 1];
+        } else {
+            shard_range(m, g, n_dev, &s, &e);
+        }
+        if (e == s) return B200BO_OK;
+        return run_host(&specs[g], Xc + (size_t)s * d, e - s, acq_neg + s, nullptr, nullptr, 0, nullptr, nullptr);
+    });
 }

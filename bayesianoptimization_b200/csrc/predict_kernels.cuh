@@ -22,6 +22,7 @@
 // independent of the grid size.
 #pragma once
 #include "common.cuh"
+#include "select.cuh"
 #include "tc_common.cuh"
 
 namespace b200bo {
@@ -41,7 +42,12 @@ struct PredictParams {
     GpDev gp[B200BO_MAX_GPS];
     int n_gps, d, acq_kind, pad0;
     double kappa, xi, y_max;
-    const double* Xc;  // [m][d]
+    const double* Xc;  // [m][d], or nullptr: candidates generated in-kernel (Philox, select.cuh)
+    const double* pbounds;  // Philox mode: [2][d] = lo_j, (hi_j - lo_j)
+    unsigned long long seed;  // Philox key
+    long long index_base;  // global index of this launch's candidate 0 (Philox row / selection index)
+    SelList* sel_cta;  // [gridDim.x] per-CTA running selection, or nullptr (no fused selection)
+    int sel_k, sel_resume;  // resume: continue the lists of the previous launch (chunked batches)
     long long m;
     double* acq_out;   // [m] or nullptr
     double* mu_out;    // [m] or nullptr (target GP)
@@ -50,6 +56,12 @@ struct PredictParams {
     long long scratch_stride;
     unsigned long long* clamp_count;  // nullable
 };
+
+// coordinate j of candidate gi (local index) as the reference's x_tries[gi, j]
+__device__ __forceinline__ double candidate_coord(const PredictParams& P, long long gi, int j) {
+    if (P.Xc) return P.Xc[gi * P.d + j];
+    return philox_coord(P.seed, gi + P.index_base, j, P.pbounds[j], P.pbounds[P.d + j]);
+}
 
 constexpr int PBM = 128, PBN = 128, PBK = 16, PSTAGES = 3, PNT = 256;
 // smem row stride (doubles) of the A/B k-tiles.  DFMA variant: dense rows (conflict-free 16-byte
@@ -76,7 +88,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // g >= 1: constraint GP -> probability factor.  The last GP writes -base * prod.
 __device__ __forceinline__ void candidate_epilogue(const PredictParams& P, const GpDev& G, int g,
                                                    double mu_n, double colsq, long long gi,
-                                                   double& base_neg, double& prod) {
+                                                   double& base_neg, double& prod, double* final_val = nullptr) {
     const double mean = G.y_std * mu_n + G.y_mean;
     double var = G.constv - colsq;
     if (var < 0.0) {
@@ -108,8 +120,11 @@ __device__ __forceinline__ void candidate_epilogue(const PredictParams& P, const
         // constraint.py:208 (J=1: result = p_hi - p_lo) / :219 (result *= ...)
         prod = (g == 1) ? (p_hi - p_lo) : prod * (p_hi - p_lo);
     }
-    if (g == P.n_gps - 1 && P.acq_out && gi < P.m)
-        P.acq_out[gi] = (P.n_gps > 1) ? base_neg * prod : base_neg;
+    if (g == P.n_gps - 1) {
+        const double val = (P.n_gps > 1) ? base_neg * prod : base_neg;
+        if (final_val) *final_val = val;
+        if (P.acq_out && gi < P.m) P.acq_out[gi] = val;
+    }
 }
 
 // ---- phase A: K*^T tile (np x 128) into the CTA's scratch + K* alpha_ ---------------------------
@@ -136,7 +151,7 @@ __device__ __forceinline__ void predict_phase_a_impl(const PredictParams& P, con
         const long long gi = c0 + c;
         double v = 0.0;
         if (gi < P.m) {
-            v = P.Xc[gi * d + j];
+            v = candidate_coord(P, gi, j);
             if (G.xform && G.xform[j] == B200BO_XFORM_ROUND) v = rint(v);
             v = v / G.ls[j];
         }
@@ -457,11 +472,16 @@ __global__ void __launch_bounds__(PNT, 1) predict_acq_kernel(const PredictParams
     __shared__ double mu_s[2][PBN];
     __shared__ double base_s[PBN];
     __shared__ double prod_s[PBN];
+    __shared__ SelShared sel_s;
 
     const int tid = threadIdx.x;
     double* Ks = P.scratch + (long long)blockIdx.x * P.scratch_stride;
     const long long ntiles = (P.m + PBN - 1) / PBN;
     constexpr int NRED = (IMPL == PREDICT_IMPL_DMMA) ? 4 : 16;
+    if (P.sel_cta) {
+        if (tid < PBN) runsel_begin(sel_s, P.sel_cta + blockIdx.x, P.sel_resume, tid);
+        __syncthreads();
+    }
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long c0 = tile * PBN;
@@ -480,11 +500,15 @@ __global__ void __launch_bounds__(PNT, 1) predict_acq_kernel(const PredictParams
                 double colsq = 0.0;
 #pragma unroll
                 for (int r = 0; r < NRED; ++r) colsq += red[r * PBN + c];
-                candidate_epilogue(P, G, g, mu_s[0][c] + mu_s[1][c], colsq, c0 + c, base_s[c], prod_s[c]);
+                double val = 0.0;
+                candidate_epilogue(P, G, g, mu_s[0][c] + mu_s[1][c], colsq, c0 + c, base_s[c], prod_s[c], &val);
+                if (P.sel_cta && g == P.n_gps - 1)
+                    runsel_update<1>(sel_s, P.sel_k, tid, val, c0 + c + P.index_base, c0 + c < P.m);
             }
             __syncthreads();
         }
     }
+    if (P.sel_cta && tid < PBN) runsel_store(sel_s, P.sel_cta + blockIdx.x, tid);
 }
 
 // =======================================================================================
@@ -515,11 +539,16 @@ __global__ void __launch_bounds__(PNT, 1) predict_acq_tc_kernel(const PredictPar
     __shared__ double red_s[4][PBN];
     __shared__ uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], accfull_bar[2], accempty_bar[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ SelShared sel_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t* stage_mem = reinterpret_cast<uint8_t*>(smem);
     double* Ks = P.scratch + (long long)blockIdx.x * P.scratch_stride;  // holds the B images (bytes)
     const long long ntiles = (P.m + PBN - 1) / PBN;
+    if (P.sel_cta) {
+        if (tid < PBN) runsel_begin(sel_s, P.sel_cta + blockIdx.x, P.sel_resume, tid);
+        __syncthreads();
+    }
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -658,12 +687,16 @@ __global__ void __launch_bounds__(PNT, 1) predict_acq_tc_kernel(const PredictPar
             if (tid < PBN) {
                 const int c = tid;
                 const double colsq = ((red_s[0][c] + red_s[1][c]) + red_s[2][c]) + red_s[3][c];
-                candidate_epilogue(P, G, g, mu_s[0][c] + mu_s[1][c], colsq, c0 + c, base_s[c], prod_s[c]);
+                double val = 0.0;
+                candidate_epilogue(P, G, g, mu_s[0][c] + mu_s[1][c], colsq, c0 + c, base_s[c], prod_s[c], &val);
+                if (P.sel_cta && g == P.n_gps - 1)
+                    runsel_update<1>(sel_s, P.sel_k, tid, val, c0 + c + P.index_base, c0 + c < P.m);
             }
             tc::fence_proxy_async_smem();
             __syncthreads();
         }
     }
+    if (P.sel_cta && tid < PBN) runsel_store(sel_s, P.sel_cta + blockIdx.x, tid);
     tc::tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc(tmem_base, TC_TMEM_COLS);
@@ -697,7 +730,7 @@ __device__ __forceinline__ void tc2_build_job(const PredictParams& P, const GpDe
         for (int j = 0; j < kPredictMaxDimRegs; ++j) {
             double v = 0.0;
             if (j < d && gi < P.m) {
-                v = P.Xc[gi * d + j];
+                v = candidate_coord(P, gi, j);
                 if (G.xform && G.xform[j] == B200BO_XFORM_ROUND) v = rint(v);
                 v = v / G.ls[j];
             }
@@ -794,6 +827,7 @@ __global__ void __launch_bounds__(TC2_NT, 1) predict_acq_tc2_kernel(const Predic
     __shared__ uint64_t full_bar[TC2_STAGES], empty_bar[TC2_STAGES], accfull_bar[2], accempty_bar[2];
     __shared__ uint64_t bready_bar[2], jobdone_bar[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ SelShared sel_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t* stage_mem = reinterpret_cast<uint8_t*>(smem);
@@ -919,6 +953,10 @@ __global__ void __launch_bounds__(TC2_NT, 1) predict_acq_tc2_kernel(const Predic
         const int q = warp & 3, etid = tid - 128;
         uint32_t ai = 0;
         double base_neg = 0.0, prod = 1.0;
+        if (P.sel_cta) {
+            runsel_begin(sel_s, P.sel_cta + blockIdx.x, P.sel_resume, etid);
+            tc::named_bar_sync(1, 128);
+        }
         for (long long j = 0; j < njobs; ++j) {
             const int g = (int)(j % P.n_gps);
             const GpDev& G = P.gp[g];
@@ -969,12 +1007,16 @@ __global__ void __launch_bounds__(TC2_NT, 1) predict_acq_tc2_kernel(const Predic
             const double colsq =
                 (((double)red_s[0][etid] + (double)red_s[1][etid]) + (double)red_s[2][etid]) + (double)red_s[3][etid];
             tc::mbar_wait(&bready_bar[j & 1], (uint32_t)((j >> 1) & 1));  // acquire the builders' mean
+            double val = 0.0;
             candidate_epilogue(P, G, g, mu_s[j & 1][0][etid] + mu_s[j & 1][1][etid], colsq, tile * PBN + etid,
-                               base_neg, prod);
+                               base_neg, prod, &val);
+            if (P.sel_cta && g == P.n_gps - 1)
+                runsel_update<1>(sel_s, P.sel_k, etid, val, tile * PBN + etid + P.index_base, tile * PBN + etid < P.m);
             tc::named_bar_sync(1, 128);
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&jobdone_bar[j & 1]);
         }
+        if (P.sel_cta) runsel_store(sel_s, P.sel_cta + blockIdx.x, etid);
     } else if (warp >= 8) {
         // ------------------------------ builders ---------------------------------------------
         const int btid = tid - 256;
@@ -1062,7 +1104,7 @@ small_kstar_kernel(const SmallParams S, int g) {
         const int c = idx / d, j = idx - c * d;
         double v = 0.0;
         if (c < S.mc) {
-            v = S.P.Xc[(S.c0 + c) * d + j];
+            v = candidate_coord(S.P, S.c0 + c, j);
             if (G.xform && G.xform[j] == B200BO_XFORM_ROUND) v = rint(v);
             v = v / G.ls[j];
         }
@@ -1175,11 +1217,6 @@ small_finish_kernel(const SmallParams S) {
 // distinct values).  Single CTA of 1024 threads; k+1 fixed-order passes over vals (L2).
 // (R/bayes_opt/acquisition.py:313-317)
 // ---------------------------------------------------------------------------------------
-struct SelRecord {
-    double value;
-    long long index;
-};
-
 __global__ void __launch_bounds__(1024)
 select_kernel(const double* __restrict__ vals, long long m, int k, SelRecord* __restrict__ out,
               long long index_base) {

@@ -26,7 +26,24 @@ from sklearn.utils import check_random_state
 from sklearn.utils.optimize import _check_optimize_result
 
 from . import _lib as B
-from .kernels import find_transform
+
+
+def find_transform(kernel):
+    """Input transform of a kernel produced by bayes_opt's ``wrap_kernel`` (R/bayes_opt/parameter.py:457-495),
+    else None.  The reference keeps ``transform`` in the closure of the generated class (the ``_transform``
+    attribute it also sets does not survive ``sklearn.base.clone``), so both places are searched."""
+    t = getattr(kernel, "_transform", None)
+    if t is not None:
+        return t
+    call = type(kernel).__dict__.get("__call__")
+    code = getattr(call, "__code__", None)
+    if code is not None and call.__closure__:
+        for name, cell in zip(code.co_freevars, call.__closure__):
+            if name == "transform":
+                return cell.cell_contents
+    if type(kernel).__name__ == "WrappedKernel":
+        raise NotImplementedError("wrapped kernel whose transform cannot be located")
+    return None
 
 
 # --------------------------------------------------------------------------------------------
@@ -168,6 +185,15 @@ def apply_transform(mode, arg, X):
     return X
 
 
+def to_b200_gp(gp, device=0, devices=None, precision="fp64"):
+    """A B200GaussianProcessRegressor with the hyper-parameters, kernel object and RandomState of a
+    sklearn GaussianProcessRegressor (the object the reference builds privately)."""
+    if isinstance(gp, B200GaussianProcessRegressor):
+        return gp
+    return B200GaussianProcessRegressor(device=device, devices=devices, precision=precision,
+                                        **gp.get_params(deep=False))
+
+
 class _Handle:
     """Owns one b200bo_gp*."""
 
@@ -187,7 +213,9 @@ class _Handle:
 class B200GaussianProcessRegressor(GaussianProcessRegressor):
     """GaussianProcessRegressor whose numerics run on a B200 (fp64).
 
-    Same constructor as sklearn's plus ``device`` (CUDA ordinal) and ``precision``: "fp64" (exact,
+    Same constructor as sklearn's plus ``device`` (CUDA ordinal of the fit), ``devices`` (optional list of
+    ordinals: the fitted state is replicated there and large acquisition batches / the L-BFGS-B seeds are
+    sharded over them) and ``precision``: "fp64" (exact,
     parity 1e-5, default) or "fp32" (the N^2 term of predict on tcgen05 tensor cores as 3xTF32 with
     fp32 accumulation; fit, K*, the mean and the acquisition epilogue stay fp64; tolerance 1e-3).  ``fit`` mirrors
     SK/gaussian_process/_gpr.py:233-368 (incl. the 1 + n_restarts_optimizer L-BFGS-B runs and the
@@ -197,12 +225,13 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
 
     def __init__(self, kernel=None, *, alpha=1e-10, optimizer="fmin_l_bfgs_b", n_restarts_optimizer=0,
                  normalize_y=False, copy_X_train=True, n_targets=None, random_state=None, device=0,
-                 precision="fp64"):
+                 precision="fp64", devices=None):
         super().__init__(kernel=kernel, alpha=alpha, optimizer=optimizer,
                          n_restarts_optimizer=n_restarts_optimizer, normalize_y=normalize_y,
                          copy_X_train=copy_X_train, n_targets=n_targets, random_state=random_state)
         self.device = device
         self.precision = precision
+        self.devices = devices  # optional list of CUDA ordinals: predict/acquisition batches shard over them
 
     # ---- device plumbing -----------------------------------------------------------------
     def _handle(self) -> _Handle:
@@ -217,6 +246,7 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
         state = dict(state)
         state.pop("_b200_handle", None)
         state.pop("_b200_restart_handles", None)
+        state.pop("_b200_replicas", None)
         state["_b200_device_fitted"] = False
         return state
 
@@ -252,6 +282,35 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
         self.__dict__["_b200_device_fitted"] = True
         self.__dict__.pop("_b200_L", None)
         self.__dict__.pop("_b200_alpha", None)
+        self.__dict__.pop("_b200_replicas", None)
+
+    def device_list(self):
+        """CUDA ordinals this GP evaluates on: [device] or the ``devices`` option (fit device first)."""
+        if not self.devices:
+            return [int(self.device)]
+        devs = [int(x) for x in self.devices]
+        if int(self.device) in devs:
+            devs.remove(int(self.device))
+        return [int(self.device)] + devs
+
+    def _device_handles(self):
+        """One fitted handle per device of device_list(): the primary plus replicas of its fitted state
+        (b200bo_gp_replicate: peer copies of Xs, L^-1, alpha_ over NVLink; no re-factorisation)."""
+        self._ensure_device_fit()
+        devs = self.device_list()
+        main = self._handle()
+        if len(devs) == 1:
+            return [main]
+        reps = self.__dict__.get("_b200_replicas")
+        if reps is None or [d for d, _ in reps] != devs[1:]:
+            reps = []
+            for dv in devs[1:]:
+                h = _Handle.__new__(_Handle)
+                h.ptr = C.c_void_p()
+                B.check(B.lib().b200bo_gp_replicate(main.ptr, int(dv), C.byref(h.ptr)))
+                reps.append((dv, h))
+            self.__dict__["_b200_replicas"] = reps
+        return [main] + [h for _, h in reps]
 
     # sklearn exposes L_ and alpha_ as attributes; materialise them lazily from the device
     @property
@@ -291,7 +350,10 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
         else:
             self.kernel_ = clone(self.kernel)
         self._rng = check_random_state(self.random_state)
-        X = np.array(X, dtype=np.float64, ndmin=2, copy=True)
+        X = np.array(X, dtype=np.float64, copy=True)
+        if X.ndim != 2:  # sklearn's validate_data rejects the same inputs
+            raise ValueError(f"Expected 2D array, got {X.ndim}D array instead: reshape your data with "
+                             "array.reshape(-1, 1) for a single feature or array.reshape(1, -1) for a single sample.")
         y = np.asarray(y, dtype=np.float64)
         if y.ndim == 2 and y.shape[1] == 1:
             y = y[:, 0]
@@ -358,12 +420,20 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
                                      "requires that all bounds are finite.")
                 for _ in range(self.n_restarts_optimizer):
                     starts.append(self._rng.uniform(bounds[:, 0], bounds[:, 1]))
-            workers = self._restart_workers(len(starts), Xd, y, codes)
-            if workers is None:
-                obj_func = make_obj(h)
-                optima = [self._constrained_optimization(obj_func, t0, bounds) for t0 in starts]
-            else:
-                optima = self._run_restarts_concurrently(workers, make_obj, starts, bounds)
+            try:
+                workers = self._restart_workers(len(starts), Xd, y, codes)
+            except B.B200Error:  # e.g. out of memory for the worker buffers: sequential loop
+                workers = None
+                L.b200bo_gp_set_private_stream(h.ptr, 0)
+            try:
+                if workers is None:
+                    obj_func = make_obj(h)
+                    optima = [self._constrained_optimization(obj_func, t0, bounds) for t0 in starts]
+                else:
+                    optima = self._run_restarts_concurrently(workers, make_obj, starts, bounds)
+            finally:
+                # worker handles hold 5 N^2 doubles each: never keep them between suggest() calls
+                self.__dict__.pop("_b200_restart_handles", None)
             lml_values = list(map(itemgetter(1), optima))
             self.kernel_.theta = optima[np.argmin(lml_values)][0]
             self.kernel_._check_bounds_params()
@@ -373,8 +443,22 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
         else:
             if not self._try_incremental(prev, X, y, ek):
                 self._device_fit(ek)
-            self.log_marginal_likelihood_value_ = None  # computed on demand (costs one more factorisation)
+            self.__dict__["_b200_lml_value"] = None  # computed on first access (one more factorisation)
         return self
+
+    # sklearn always leaves a float here; with optimizer=None it costs one extra factorisation, so the
+    # value is produced on first access instead of inside every fit()
+    @property
+    def log_marginal_likelihood_value_(self):
+        v = self.__dict__.get("_b200_lml_value")
+        if v is None and hasattr(self, "X_train_"):
+            v = self.log_marginal_likelihood(self.kernel_.theta, clone_kernel=True)
+            self.__dict__["_b200_lml_value"] = v
+        return v
+
+    @log_marginal_likelihood_value_.setter
+    def log_marginal_likelihood_value_(self, v):
+        self.__dict__["_b200_lml_value"] = v
 
     # ---- concurrent restarts -----------------------------------------------------------------
     _MAX_RESTART_WORKERS = 8
@@ -504,9 +588,6 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
         if theta is None:
             if eval_gradient:
                 raise ValueError("Gradient can only be evaluated for theta!=None")
-            if getattr(self, "log_marginal_likelihood_value_", None) is None:
-                self.log_marginal_likelihood_value_ = self.log_marginal_likelihood(
-                    self.kernel_.theta, clone_kernel=True)
             return self.log_marginal_likelihood_value_
         if clone_kernel:
             kernel = self.kernel_.clone_with_theta(theta)
@@ -530,7 +611,10 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
         """SK/gaussian_process/_gpr.py:370-500 (return_std path) on the device."""
         if return_std and return_cov:
             raise RuntimeError("At most one of return_std or return_cov can be requested.")
-        X = np.array(X, dtype=np.float64, ndmin=2)
+        X = np.array(X, dtype=np.float64)
+        if X.ndim != 2:
+            raise ValueError(f"Expected 2D array, got {X.ndim}D array instead: reshape your data with "
+                             "array.reshape(-1, 1) for a single feature or array.reshape(1, -1) for a single sample.")
         if not np.all(np.isfinite(X)):
             raise ValueError("Input contains NaN or infinity.")
         if not hasattr(self, "X_train_"):  # unfitted: GP prior (:417-443), no device work to do

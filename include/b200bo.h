@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200BO_VERSION 100 /* 0.1.0 */
+#define B200BO_VERSION 200 /* 0.2.0 */
 
 /* error codes */
 #define B200BO_OK 0
@@ -77,9 +77,18 @@ typedef struct {
 
 /* One acquisition evaluation: the closure built by AcquisitionFunction._get_acq
  * (R/bayes_opt/acquisition.py:171-219):  -base_acq(mu, sigma) [* prod_j p_j(x)]. */
+/* Which kernels evaluate a batch.  AUTO: the tiled persistent kernel or the small-batch kernels, chosen
+ * from the batch size m.  STABLE: chosen from the model size only - an optimiser's objective f(x) and its
+ * finite-difference stencil f(x + h e_i) arrive as batches of different sizes and must be summed in the same
+ * order (SP/optimize/_numdiff.py forms (f(x+h) - f(x)) / 1.5e-8). */
+#define B200BO_PATH_AUTO 0
+#define B200BO_PATH_STABLE 1
+
 typedef struct {
     int32_t kind;              /* B200BO_ACQ_* */
     int32_t n_gps;             /* 1 + number of constraint GPs */
+    int32_t path;              /* B200BO_PATH_* */
+    int32_t reserved;
     double kappa;              /* UCB */
     double xi;                 /* EI / PoI */
     double y_max;              /* EI / PoI */
@@ -189,6 +198,51 @@ int b200bo_acq_argmin_topk(const b200bo_acq* spec, const double* Xc, int64_t m, 
 int b200bo_acq_eval_dev(const b200bo_acq* spec, const double* d_Xc, int64_t m,
                         double* d_acq_neg, double* d_mu, double* d_sd, int k, void* d_sel,
                         int64_t index_base, void* stream);
+
+/* ---- throughput mode: device-side candidate source ------------------------------------ */
+/* The reference draws the M candidates on the host (TargetSpace.random_sample, R/bayes_opt/target_space.py:
+ * 565-603: column j = rng.uniform(lo_j, hi_j, M) from MT19937) - ~10^8 doubles/s, slower than the fp32-mode
+ * kernel consumes them.  In throughput mode candidate i, column j is  lo_j + (hi_j - lo_j) * u,  u the 53-bit
+ * uniform from Philox4x32-10 with counter (i + index_base, j/2) and key `seed`, generated INSIDE the fused
+ * kernel: the candidate matrix never exists in host memory or HBM.  Rows depend only on (seed, global index),
+ * so results are identical for any tiling and any number of GPUs.  This is an opt-in mode: it does not
+ * reproduce the reference's RNG stream (parity mode = the host entry points above).
+ * lo, hi: (d,) host.  best_x: (d,), topk_x: (k,d) host - the winners' coordinates, regenerated on the device. */
+int b200bo_acq_argmin_topk_philox(const b200bo_acq* spec, uint64_t seed, const double* lo, const double* hi,
+                                  int64_t m, int64_t index_base, int k, double* best_val, int64_t* best_idx,
+                                  double* best_x, double* topk_val, int64_t* topk_idx, double* topk_x);
+/* Device-resident flavour: only the (k+1) selection records are produced (d_sel as in b200bo_acq_eval_dev). */
+int b200bo_acq_select_philox_dev(const b200bo_acq* spec, uint64_t seed, const double* lo, const double* hi,
+                                 int64_t m, int64_t index_base, int k, void* d_sel, void* stream);
+/* Rows of the Philox candidate matrix for given global indices (idx < 0 -> NaN row).  out: (n_idx, d) host. */
+int b200bo_philox_rows(int device, uint64_t seed, const double* lo, const double* hi, int d,
+                       const int64_t* idx, int64_t n_idx, double* out);
+
+/* ---- multi-GPU (one process, several devices of one box) -------------------------------- */
+/* candidates are independent given the model, so a batch shards by rows over G devices, the
+ * O(N^2) model state is replicated, and ONE exchange merges the per-device (argmin, top-k) records:
+ * an ncclAllGather of (k+1) 16-byte records per device over NVLink (communicators from ncclCommInitAll,
+ * created on first use for a device list and cached), then a merge kernel on device 0.  The reference has no
+ * counterpart (single process, single thread: R/bayes_opt/acquisition.py:274-320).
+ *
+ * b200bo_gp_replicate: copy the fitted state of `src` (what predict needs: scaled X, L^-1, alpha_, statistics)
+ * to a new handle on `device` with peer copies - no re-factorisation.  The replica is predict-only. */
+int b200bo_gp_replicate(const b200bo_gp* src, int device, b200bo_gp** out);
+/* specs[g] is the acquisition on device g (its gps[] are handles living on ONE device; all specs describe the
+ * same model).  Rows [m*g/G, m*(g+1)/G) go to device g (remainder to the low devices); results as
+ * b200bo_acq_argmin_topk with GLOBAL row indices - bit-identical to the single-device call. */
+int b200bo_multi_gpu_acq_argmin_topk(const b200bo_acq* specs, int n_dev, const double* Xc, int64_t m, int k,
+                                     double* best_val, int64_t* best_idx, double* topk_val,
+                                     int64_t* topk_idx);
+int b200bo_multi_gpu_acq_argmin_topk_philox(const b200bo_acq* specs, int n_dev, uint64_t seed, const double* lo,
+                                            const double* hi, int64_t m, int64_t index_base, int k,
+                                            double* best_val, int64_t* best_idx, double* best_x,
+                                            double* topk_val, int64_t* topk_idx, double* topk_x);
+/* Closure values for a batch split over the devices: rows [offsets[g], offsets[g+1]) on device g
+ * (offsets: (n_dev+1,) host, or NULL for an even split).  Used by the lockstep L-BFGS-B driver to run seed r's
+ * requests on device r mod G (R/bayes_opt/acquisition.py:364-374).  No collective. */
+int b200bo_multi_gpu_acq_eval(const b200bo_acq* specs, int n_dev, const double* Xc, int64_t m,
+                              const int64_t* offsets, double* acq_neg);
 
 /* Duration (ms) of the most recent fused predict+acquisition kernel launched through a
  * device or host entry point on this thread, measured with CUDA events on its stream.

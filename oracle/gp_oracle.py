@@ -279,3 +279,47 @@ def argmin_topk(ys, k):
     i = int(np.argmin(ys))
     order = np.argsort(ys, kind="stable")[:k]
     return i, float(ys[i]), order
+
+
+# ---------------------------------------------------------------------------------------------------
+# Throughput-mode candidate source: Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers:
+# as easy as 1, 2, 3", SC'11), restated with numpy uint64 arithmetic.  The reference has no counterpart
+# (it draws candidates from MT19937 on the host, R/bayes_opt/target_space.py:565-603); this pins the CUDA
+# generator in csrc/select.cuh bit for bit:
+#   counter = (row_lo32, row_hi32, col // 2, 0), key = (seed_lo32, seed_hi32)
+#   word    = o0 | o1 << 32 (even col) or o2 | o3 << 32 (odd col);  u = (word >> 11) * 2^-53
+#   x       = lo + (hi - lo) * u      (two roundings)
+# ---------------------------------------------------------------------------------------------------
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    W0, W1 = np.uint64(0x9E3779B9), np.uint64(0xBB67AE85)
+    mask = np.uint64(0xFFFFFFFF)
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & mask for c in (c0, c1, c2, c3))
+    k0, k1 = np.uint64(k0) & mask, np.uint64(k1) & mask
+    s32 = np.uint64(32)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2  # 32x32 -> 64 bit products (no overflow in uint64)
+        c0, c1, c2, c3 = ((p1 >> s32) ^ c1 ^ k0) & mask, p1 & mask, ((p0 >> s32) ^ c3 ^ k1) & mask, p0 & mask
+        k0, k1 = (k0 + W0) & mask, (k1 + W1) & mask
+    return c0, c1, c2, c3
+
+
+def philox_uniform(seed, rows, d, lo, hi):
+    """Candidate rows `rows` (global indices) of the throughput-mode matrix: shape (len(rows), d)."""
+    rows = np.asarray(rows, dtype=np.int64).astype(np.uint64)
+    lo, hi = np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    out = np.empty((len(rows), d))
+    with np.errstate(over="ignore"):
+        for b in range((d + 1) // 2):
+            o0, o1, o2, o3 = philox4x32_10(rows & np.uint64(0xFFFFFFFF), rows >> np.uint64(32),
+                                           np.full(len(rows), b, dtype=np.uint64), np.zeros(len(rows), dtype=np.uint64),
+                                           seed & 0xFFFFFFFF, seed >> 32)
+            for half, (a, bb) in enumerate(((o0, o1), (o2, o3))):
+                j = 2 * b + half
+                if j >= d:
+                    break
+                w = a | (bb << np.uint64(32))
+                u = (w >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+                out[:, j] = lo[j] + (hi[j] - lo[j]) * u
+    return out

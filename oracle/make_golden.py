@@ -279,13 +279,45 @@ def case_categorical():
          mu=mu, sd=sd, X_transformed=space.kernel_transform(space.params))
 
 
+def case_gphedge():
+    """GPHedge (R/bayes_opt/acquisition.py:1181-1360) over UCB / EI / PoI: four suggest() calls at fixed
+    hyper-parameters (fit_gp=False on a GP re-fitted with optimizer=None before every call), so that the
+    gains (cumulative posterior means of the previous candidates, :1236-1252), the softmax draw (:1222-1234)
+    and the three base suggestions are pinned tightly."""
+    def f(x, y):
+        return -((x - 3) ** 2) - (y - 1) ** 2 + 0.3 * np.sin(3 * x)
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        space = TargetSpace(f, {"x": (1, 4), "y": (0, 3.0)})
+        rs = RandomState(2)
+        for _ in range(7):
+            space.probe(space.random_sample(random_state=rs))
+        X0, y0 = space.params.copy(), space.target.copy()
+        gp = GaussianProcessRegressor(
+            kernel=wrap_kernel(Matern(nu=2.5, length_scale=0.9), space.kernel_transform), alpha=1e-6,
+            normalize_y=True, optimizer=None)
+        hedge = acquisition.GPHedge([acquisition.UpperConfidenceBound(kappa=2.0),
+                                     acquisition.ExpectedImprovement(xi=0.01),
+                                     acquisition.ProbabilityOfImprovement(xi=0.01)])
+        rng = RandomState(13)
+        sugg, gains, cands = [], [], []
+        for _ in range(4):
+            gp.fit(space.params, space.target)
+            x = hedge.suggest(gp, space, n_random=3000, n_smart=3, fit_gp=False, random_state=rng)
+            sugg.append(x)
+            gains.append(hedge.gains.copy())
+            cands.append(hedge.previous_candidates.copy())
+            space.probe(x)
+    save("gphedge_small", X=X0, y=y0, suggestions=np.array(sugg), gains=np.array(gains), candidates=np.array(cands),
+         next_rand=np.float64(rng.rand()))
+
+
+CASES = dict(readme=case_readme, ei=case_ei, kernels=case_kernels, constrained=case_constrained,
+             fit_full=case_fit_full, constant_liar=case_constant_liar, mixed_int=case_mixed_int,
+             categorical=case_categorical, gphedge=case_gphedge)
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    case_readme()
-    case_ei()
-    case_kernels()
-    case_constrained()
-    case_fit_full()
-    case_constant_liar()
-    case_mixed_int()
-    case_categorical()
+    for name in (sys.argv[1:] or list(CASES)):  # no arguments: regenerate everything
+        CASES[name]()

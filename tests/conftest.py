@@ -9,6 +9,19 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# The reference package (bayes_opt) drives the drop-in tests.  It is vendored, unmodified, into the
+# git-ignored oracle/_ref by tools/vendor_ref.py (here, where /root/reference exists) and travels to the GPU
+# box with the snapshot; the product package imports `bayes_opt` from sys.path like any user environment.
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+try:
+    import vendor_ref
+
+    _REF = vendor_ref.vendor()
+except Exception:  # pragma: no cover
+    _REF = None
+if _REF and _REF not in sys.path:
+    sys.path.insert(0, _REF)
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
@@ -41,3 +54,13 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The unmodified reference package."""
+    try:
+        import bayes_opt
+    except ImportError:
+        pytest.skip("reference package bayes_opt not importable (run tools/vendor_ref.py where /root/reference exists)")
+    return bayes_opt

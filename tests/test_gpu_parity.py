@@ -22,6 +22,12 @@ def bo():
 
 
 @pytest.fixture(scope="module")
+def TS(ref):
+    """The reference's TargetSpace (the hooks consume its RNG stream and bounds)."""
+    return ref.target_space.TargetSpace
+
+
+@pytest.fixture(scope="module")
 def O():
     from oracle import gp_oracle
 
@@ -461,7 +467,7 @@ def test_small_batch_path_vs_tiled_and_oracle(bo, O, n, d, monkeypatch):
         assert idx == int(np.argmin(out["1"][0]))
 
 
-def test_batched_fd_stencil_matches_sequential_lbfgsb(bo, golden):
+def test_batched_fd_stencil_matches_sequential_lbfgsb(bo, golden, TS):
     """_smart_minimize with the batched stencil map follows the same iterates as plain SciPy
     L-BFGS-B with one objective call per stencil point (R/bayes_opt/acquisition.py:366)."""
     from scipy.optimize import minimize
@@ -471,7 +477,7 @@ def test_batched_fd_stencil_matches_sequential_lbfgsb(bo, golden):
     a = bo.ExpectedImprovement(xi=float(g["xi"]))
     a.y_max = float(g["y_max"])
     f = a._get_acq(gp=gp)
-    space = bo.TargetSpace(None, {f"x{i:02d}": (0.0, 1.0) for i in range(8)})
+    space = TS(None, {f"x{i:02d}": (0.0, 1.0) for i in range(8)})
     seeds = g["xt"][g["top10"][:3]]
     x_b, v_b = a._smart_minimize(f, space, seeds, np.random.RandomState(0))
     best = None
@@ -600,7 +606,7 @@ def test_round_transform_for_int_parameters(bo, O):
         v[:, 1] = np.round(v[:, 1])
         return v
 
-    from bayesianoptimization_b200.kernels import wrap_kernel
+    from bayes_opt.parameter import wrap_kernel
 
     gp = make_gp(bo, wrap_kernel(Matern(nu=2.5, length_scale=0.8), transform)).fit(X, y)
     xt = np.column_stack([rs.uniform(0, 1, 500), rs.uniform(0, 10, 500)])
@@ -679,11 +685,11 @@ def test_device_resident_entry_point(bo, golden):
 # ------------------------------------------------------------------------------------------
 # end-to-end suggest()
 # ------------------------------------------------------------------------------------------
-def test_suggest_end_to_end_readme(bo, golden):
+def test_suggest_end_to_end_readme(bo, golden, TS):
     """Full suggest() (fit with 5 restarts + 10k candidates + 10 L-BFGS-B refinements) from the
     reference's RNG state: end-to-end tier - same point to optimiser tolerance."""
     g = golden("c1_readme_ucb")
-    space = bo.TargetSpace(None, {"x": (2, 4), "y": (-3, 3)})
+    space = TS(None, {"x": (2, 4), "y": (-3, 3)})
     for x, t in zip(g["X"], g["y"]):
         space.register(x, t)
     rs = np.random.RandomState()
@@ -700,9 +706,9 @@ def test_suggest_end_to_end_readme(bo, golden):
     assert np.array_equal(x1, x2)
 
 
-def test_constant_liar_vs_golden(bo, golden):
+def test_constant_liar_vs_golden(bo, golden, TS):
     g = golden("constant_liar_small")
-    space = bo.TargetSpace(lambda x, y: -((x - 3) ** 2) - (y - 1) ** 2, {"x": (1, 4), "y": (0, 3.0)})
+    space = TS(lambda x, y: -((x - 3) ** 2) - (y - 1) ** 2, {"x": (1, 4), "y": (0, 3.0)})
     for x, t in zip(g["X"], g["y"]):
         space.register(x, t)
     gp = bo.B200GaussianProcessRegressor(kernel=Matern(nu=2.5), alpha=1e-6, normalize_y=True,
@@ -714,12 +720,14 @@ def test_constant_liar_vs_golden(bo, golden):
     assert len(cl.dummies) == 4
 
 
-def test_constrained_suggest_runs_and_respects_errors(bo):
-    from bayesianoptimization_b200.exception import ConstraintNotSupportedError, TargetSpaceEmptyError
+def test_constrained_suggest_runs_and_respects_errors(bo, TS):
+    from bayes_opt.exception import ConstraintNotSupportedError, TargetSpaceEmptyError
 
-    cm = bo.ConstraintModel(lambda x, y: x + y, -np.inf, 4.0)
-    space = bo.TargetSpace(lambda x, y: -((x - 3) ** 2) - (y - 1) ** 2, {"x": (1, 4), "y": (0, 3.0)},
-                           constraint=cm)
+    from scipy.optimize import NonlinearConstraint
+
+    space = TS(lambda x, y: -((x - 3) ** 2) - (y - 1) ** 2, {"x": (1, 4), "y": (0, 3.0)},
+               constraint=NonlinearConstraint(lambda x, y: x + y, -np.inf, 4.0))
+    space._constraint._model = [bo.to_b200_gp(m) for m in space._constraint._model]  # what enable() does
     gp = bo.B200GaussianProcessRegressor(kernel=Matern(nu=2.5), alpha=1e-6, normalize_y=True,
                                          n_restarts_optimizer=2, random_state=np.random.RandomState(0))
     ei = bo.ExpectedImprovement(xi=0.01)
@@ -734,9 +742,9 @@ def test_constrained_suggest_runs_and_respects_errors(bo):
         bo.UpperConfidenceBound().suggest(gp, space, random_state=rs)
 
 
-def test_gphedge_runs_and_updates_gains(bo):
+def test_gphedge_runs_and_updates_gains(bo, TS):
     """GPHedge (R/bayes_opt/acquisition.py:1181-1360) over device base acquisitions."""
-    space = bo.TargetSpace(lambda x, y: -((x - 3) ** 2) - (y - 1) ** 2, {"x": (1, 4), "y": (0, 3.0)})
+    space = TS(lambda x, y: -((x - 3) ** 2) - (y - 1) ** 2, {"x": (1, 4), "y": (0, 3.0)})
     rs = np.random.RandomState(0)
     for _ in range(6):
         space.probe(space.random_sample(random_state=rs))
@@ -758,13 +766,13 @@ def test_gphedge_runs_and_updates_gains(bo):
         hedge.base_acq(0, 1)
 
 
-def test_mixed_int_space_round_transform_and_de_branch(bo, golden):
+def test_mixed_int_space_round_transform_and_de_branch(bo, golden, TS):
     """Float + int parameters: device np.round transform vs the reference's values, then the
     DifferentialEvolution + polish branch of _smart_minimize from the same RNG state."""
-    from bayesianoptimization_b200.kernels import wrap_kernel
+    from bayes_opt.parameter import wrap_kernel
 
     g = golden("mixed_int_small")
-    space = bo.TargetSpace(None, {"x": (0.0, 5.0), "k": (0, 6, int)})
+    space = TS(None, {"x": (0.0, 5.0), "k": (0, 6, int)})
     assert np.array_equal(space.random_sample(50, np.random.RandomState(9)), g["rand_draw"])
     for x, t in zip(g["X"], g["y"]):
         space.register(x, t)
@@ -820,7 +828,7 @@ def test_categorical_parameter_host_transform(bo, golden):
     """Categorical parameter: the reference's one-hot kernel transform (batch-dependent as written,
     R/bayes_opt/parameter.py:434-449) is an opaque callable -> applied on the host to each batch,
     exactly where WrappedKernel.__call__ applies it; values must equal the reference's."""
-    from bayesianoptimization_b200.kernels import wrap_kernel
+    from bayes_opt.parameter import wrap_kernel
 
     g = golden("categorical_small")
 

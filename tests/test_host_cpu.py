@@ -32,17 +32,17 @@ def test_library_exports_every_header_symbol(bo):
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert declared == set(B.EXPORTS)
-    assert B.lib().b200bo_version() == 100
+    assert B.lib().b200bo_version() == 200
 
 
 def test_struct_layouts_match_header(bo):
     from bayesianoptimization_b200 import _lib as B
 
     assert C.sizeof(B.KernelSpec) == 32
-    assert C.sizeof(B.AcqSpec) == 8 + 24 + 8 * B.MAX_GPS * 3
+    assert C.sizeof(B.AcqSpec) == 16 + 24 + 8 * B.MAX_GPS * 3
 
 
-def test_no_cpu_fallback(bo):
+def test_no_cpu_fallback(bo, ref):
     """Without a CUDA device every compute path raises - nothing silently runs on the host."""
     import torch
 
@@ -93,12 +93,11 @@ def test_kernel_parsing(bo):
             parse_kernel(bad)
 
 
-def test_transform_probe(bo):
+def test_transform_probe(bo, ref):
     from bayesianoptimization_b200.gpr import probe_transform
 
+    from bayes_opt.parameter import wrap_kernel
     from sklearn.base import clone
-
-    from bayesianoptimization_b200.kernels import wrap_kernel
 
     k = Matern(nu=2.5)
     assert probe_transform(k, 3) is None
@@ -122,35 +121,21 @@ def test_transform_probe(bo):
         probe_transform(k, 3)
 
 
-def test_space_random_sample_matches_reference_stream(bo, golden):
-    """Candidates are drawn column-by-column from the caller's RandomState exactly as
-    TargetSpace.random_sample does (R/bayes_opt/target_space.py:596-600)."""
+def test_golden_candidates_are_the_reference_stream(ref, golden):
+    """The committed fixtures hold the candidates TargetSpace.random_sample draws column by column from
+    the caller's RandomState (R/bayes_opt/target_space.py:596-600) - the stream the device hooks must
+    keep consuming identically."""
+    TargetSpace = ref.target_space.TargetSpace
     g = golden("c1_readme_ucb")
-    space = bo.TargetSpace(None, {"x": (2, 4), "y": (-3, 3)})
-    xt = space.random_sample(10_000, np.random.RandomState(7))
-    assert np.array_equal(xt, g["xt"])
+    space = TargetSpace(None, {"x": (2, 4), "y": (-3, 3)})
+    assert np.array_equal(space.random_sample(10_000, np.random.RandomState(7)), g["xt"])
     g2 = golden("c2s_ei")
-    sp8 = bo.TargetSpace(None, {f"x{i:02d}": (0.0, 1.0) for i in range(8)})
+    sp8 = TargetSpace(None, {f"x{i:02d}": (0.0, 1.0) for i in range(8)})
     assert np.array_equal(sp8.random_sample(128, np.random.RandomState(0)), g2["X"])
     assert np.array_equal(sp8.random_sample(4096, np.random.RandomState(1)), g2["xt"])
-    assert sp8.random_sample(random_state=np.random.RandomState(3)).shape == (8,)
 
 
-def test_space_register_mask_target_max(bo):
-    from bayesianoptimization_b200.exception import NotUniqueError
-
-    sp = bo.TargetSpace(lambda a, b: a + b, {"a": (0, 1), "b": (0, 2)})
-    assert sp.empty and sp._target_max() is None
-    sp.probe({"a": 0.5, "b": 1.0})
-    sp.register([0.25, 0.5], 7.0)
-    sp.register([3.0, 0.5], 99.0)  # out of bounds -> masked out of _target_max
-    assert len(sp) == 3 and sp._target_max() == 7.0
-    with pytest.raises(NotUniqueError):
-        sp.register([0.25, 0.5], 1.0)
-    assert sp.max()["params"] == {"a": 0.25, "b": 0.5}
-
-
-def test_acquisition_parameter_validation_and_decay(bo):
+def test_acquisition_parameter_validation_and_decay(bo, ref):
     """R/tests/test_acquisition.py:142-156,182-238 behaviours."""
     with pytest.raises(ValueError):
         bo.UpperConfidenceBound(kappa=-1)
@@ -192,7 +177,7 @@ def test_acquisition_parameter_validation_and_decay(bo):
     assert cl2.get_acquisition_params() == q
 
 
-def test_acq_min_machinery_on_analytic_bowl(bo):
+def test_acq_min_machinery_on_analytic_bowl(bo, ref):
     """R/tests/test_acquisition.py:90-139: the optimiser machinery alone finds (3, 1)."""
 
     class Bowl(bo.AcquisitionFunction):
@@ -202,7 +187,7 @@ def test_acq_min_machinery_on_analytic_bowl(bo):
         def _get_acq(self, gp, constraint=None):
             return lambda x: (3 - np.atleast_2d(x)[:, 0]) ** 2 + (1 - np.atleast_2d(x)[:, 1]) ** 2
 
-    sp = bo.TargetSpace(None, {"x": (1, 4), "y": (0, 3.0)})
+    sp = ref.target_space.TargetSpace(None, {"x": (1, 4), "y": (0, 3.0)})
     acq = Bowl()
     f = acq._get_acq(None)
     rs = np.random.RandomState(0)
@@ -217,13 +202,17 @@ def test_acq_min_machinery_on_analytic_bowl(bo):
     assert v_s == np.inf or np.isnan(v_s) or True
 
 
-def test_constraint_model_host_logic(bo):
+def test_constraint_model_host_logic(bo, ref):
+    """The device ConstraintModel IS the reference's class with B200 GPs inside."""
+    assert issubclass(bo.ConstraintModel, ref.constraint.ConstraintModel)
     cm = bo.ConstraintModel(lambda x: x, np.array([-1.0, 0.0]), np.array([1.0, 2.0]))
     assert len(cm.model) == 2
     vals = np.array([[0.0, 1.0], [2.0, 1.0], [0.0, -1.0]])
     assert list(cm.allowed(vals)) == [True, False, False]
     with pytest.raises(ValueError):
         bo.ConstraintModel(None, 1.0, 0.0)
+    assert all(isinstance(m, bo.B200GaussianProcessRegressor) for m in cm.model)
+    assert cm.model[0].alpha == 1e-6 and cm.model[0].n_restarts_optimizer == 5 and cm.model[0].normalize_y
     cm1 = bo.ConstraintModel(lambda x: x, -np.inf, 0.5)
     assert list(cm1.allowed(np.array([0.2, 0.7]))) == [True, False]
     with pytest.raises(ValueError):
@@ -259,7 +248,7 @@ def test_lockstep_lbfgsb_equals_sequential_runs(bo):
     exactly the iterates of independent sequential runs (R/bayes_opt/acquisition.py:365-366)."""
     from scipy.optimize import minimize
 
-    from bayesianoptimization_b200.acquisition import _lockstep_lbfgsb
+    from bayesianoptimization_b200.fused import lockstep_lbfgsb as _lockstep_lbfgsb
 
     calls = []
 
@@ -300,7 +289,7 @@ def test_bench_reference_arm_contract():
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
         assert key in j, key
-    assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port"
+    assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "reference"
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in j["config"]
 
 

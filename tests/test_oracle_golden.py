@@ -142,3 +142,29 @@ def test_mixed_int_round_transform(golden):
     assert_allclose(sd, g["sd"], rtol=1e-8, atol=1e-11)
     ys = O.acq_closure(st, O.ACQ_EI, xi=0.01, y_max=float(g["y_max"]))(tr(g["xt"]))
     assert_allclose(ys, g["acq_ei"], rtol=1e-7, atol=1e-14)
+
+
+def test_philox_oracle_known_answer_vectors():
+    """oracle.philox4x32_10 against the published known-answer vectors of Philox4x32-10 (Random123
+    kat_vectors: counter / key all zero, all ones, digits of pi)."""
+    from oracle import gp_oracle as O
+
+    kat = [
+        ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+        ((0xFFFFFFFF,) * 4, (0xFFFFFFFF, 0xFFFFFFFF), (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+         (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+    ]
+    for ctr, key, want in kat:
+        got = O.philox4x32_10(*[[c] for c in ctr], *key)
+        assert tuple(int(g[0]) for g in got) == want
+    x = O.philox_uniform(7, [0, 1, 2**33 + 5], 3, [0, 0, -1], [1, 2, 1])
+    assert x.shape == (3, 3) and np.all(x[:, 0] >= 0) and np.all(x[:, 0] < 1) and np.all(np.abs(x[:, 2]) <= 1)
+    big = O.philox_uniform(99, np.arange(200_000), 2, [0, 0], [1, 1])
+    assert abs(big.mean() - 0.5) < 2e-3 and abs(big.var() - 1 / 12) < 2e-3
+
+
+def test_gphedge_fixture_shapes(golden):
+    g = golden("gphedge_small")
+    assert g["suggestions"].shape == (4, 2) and g["gains"].shape == (4, 3) and g["candidates"].shape == (4, 3, 2)
+    assert np.all(g["gains"][0] == 0) and np.any(g["gains"][1] != 0)
