@@ -19,8 +19,11 @@
 
 #include "fit_kernels.cuh"
 #include "predict_kernels.cuh"
+#include "predict16.cuh"
 
 using namespace b200bo;
+
+constexpr int kDefaultPredictWarps = 8;  // see DESIGN.md 4.1 (measured A/B)
 
 // ---------------------------------------------------------------------------------------
 // error plumbing
@@ -186,6 +189,11 @@ static int init_handle(b200bo_gp* gp) {
                             kPredictSmemBytesTc));
     CU(cudaFuncSetAttribute(predict_acq_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             kPredictSmemBytesTc2));
+    CU(cudaFuncSetAttribute(predict_acq16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDmma));
+    CU(cudaFuncSetAttribute(predict_acq16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDmma));
+    CU(cudaFuncSetAttribute(dgemm128_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemm128SmemBytes));
+    CU(cudaFuncSetAttribute(dgemm128_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemm128SmemBytes));
+    CU(cudaFuncSetAttribute(dgemm128_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemm128SmemBytes));
     return B200BO_OK;
 }
 
@@ -359,9 +367,17 @@ static int gemm(int M, int N, int K, double alpha, const double* A, int lda, lon
                 const double* B, int ldb, long long sB, double beta, double* C, int ldc,
                 long long sC, int batch, int lower_only, int kmode) {
     if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return B200BO_OK;
-    dim3 grid(N / 64, M / 64, batch);
-    dgemm64_kernel<TA, TB><<<grid, 256, 0, g_st>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC,
-                                          lower_only, kmode);
+    // 128x128 pipelined tiles wherever a tile can be filled; the 64x64 kernel for narrow panels / small blocks
+    static const bool force64 = [] { const char* e = getenv("B200BO_GEMM"); return e && e[0] == '6'; }();
+    if (M >= 128 && N >= 128 && !force64) {
+        dim3 grid((N + 127) / 128, (M + 127) / 128, batch);
+        dgemm128_kernel<TA, TB><<<grid, 256, kGemm128SmemBytes, g_st>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta,
+                                                                        C, ldc, sC, lower_only, kmode);
+    } else {
+        dim3 grid(N / 64, M / 64, batch);
+        dgemm64_kernel<TA, TB><<<grid, 256, 0, g_st>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC,
+                                                       lower_only, kmode);
+    }
     LAUNCHED();
     CU(cudaGetLastError());
     return B200BO_OK;
@@ -384,9 +400,14 @@ static int factorize(b200bo_gp* gp, const b200bo_kernel* kern, double jitter, in
     }
     {
         dim3 blk(32, 8), grd(np / 32, np / 32);
-        kbuild_kernel<<<grd, blk, 0, g_st>>>(gp->Xs.as<double>(), gp->K.as<double>(), n, np, d, kern->family,
-                                    kern->family == B200BO_KERNEL_RBF ? B200BO_NU_INF : kern->nu,
-                                    kern->const_value, jitter);
+        double* Kp = gp->K.as<double>();
+        const double* Xsp = gp->Xs.as<double>();
+        switch (cov_code(kern->family, kern->nu)) {
+            case 0: kbuild_kernel<0><<<grd, blk, 0, g_st>>>(Xsp, Kp, n, np, d, kern->const_value, jitter); break;
+            case 1: kbuild_kernel<1><<<grd, blk, 0, g_st>>>(Xsp, Kp, n, np, d, kern->const_value, jitter); break;
+            case 2: kbuild_kernel<2><<<grd, blk, 0, g_st>>>(Xsp, Kp, n, np, d, kern->const_value, jitter); break;
+            default: kbuild_kernel<3><<<grd, blk, 0, g_st>>>(Xsp, Kp, n, np, d, kern->const_value, jitter); break;
+        }
         LAUNCHED();
     }
     CU(cudaGetLastError());
@@ -628,13 +649,39 @@ extern "C" int b200bo_gp_lml(b200bo_gp* gp, const b200bo_kernel* kern, double al
         if ((rc = gemm<true, false>(np, np, np, 1.0, gp->W.as<double>(), np, 0, gp->W.as<double>(), np, 0,
                                     0.0, gp->T.as<double>(), np, 0, 1, 1, 3)))
             return rc;
-        dim3 grd((n + 15) / 16, (n + 15) / 16);
-        const size_t nblk = (size_t)grd.x * grd.y;
-        if ((rc = gp->part.reserve(sizeof(double) * nblk * ntheta))) return rc;
-        lml_grad_kernel<<<grd, 256, 0, g_st>>>(gp->Xs.as<double>(), gp->T.as<double>(), np, gp->alphav.as<double>(),
-                                      n, d, kern->family,
-                                      kern->family == B200BO_KERNEL_RBF ? B200BO_NU_INF : kern->nu,
-                                      kern->const_value, has_const, aniso, gp->part.as<double>(), ntheta);
+        size_t nblk;
+        const int cov = cov_code(kern->family, kern->nu);
+        if (d <= LG_DMAX) {
+            // 64x64 patches on or below the diagonal, covariance and iso/aniso as template parameters
+            const int nb64 = (n + 63) / 64;
+            dim3 grd(nb64, nb64);
+            nblk = (size_t)nb64 * (nb64 + 1) / 2;
+            if ((rc = gp->part.reserve(sizeof(double) * nblk * ntheta))) return rc;
+            const double* Xsp = gp->Xs.as<double>();
+            const double* Ki = gp->T.as<double>();
+            const double* al = gp->alphav.as<double>();
+            double* pt = gp->part.as<double>();
+#define B200BO_LG(COV)                                                                                              \
+    if (aniso)                                                                                                      \
+        lml_grad_tile_kernel<COV, true><<<grd, 256, 0, g_st>>>(Xsp, Ki, np, al, n, d, kern->const_value, has_const, pt, ntheta); \
+    else                                                                                                            \
+        lml_grad_tile_kernel<COV, false><<<grd, 256, 0, g_st>>>(Xsp, Ki, np, al, n, d, kern->const_value, has_const, pt, ntheta);
+            switch (cov) {
+                case 0: B200BO_LG(0) break;
+                case 1: B200BO_LG(1) break;
+                case 2: B200BO_LG(2) break;
+                default: B200BO_LG(3) break;
+            }
+#undef B200BO_LG
+        } else {
+            dim3 grd((n + 15) / 16, (n + 15) / 16);
+            nblk = (size_t)grd.x * grd.y;
+            if ((rc = gp->part.reserve(sizeof(double) * nblk * ntheta))) return rc;
+            lml_grad_kernel<<<grd, 256, 0, g_st>>>(gp->Xs.as<double>(), gp->T.as<double>(), np, gp->alphav.as<double>(),
+                                                   n, d, kern->family,
+                                                   kern->family == B200BO_KERNEL_RBF ? B200BO_NU_INF : kern->nu,
+                                                   kern->const_value, has_const, aniso, gp->part.as<double>(), ntheta);
+        }
         LAUNCHED();
         CU(cudaGetLastError());
         std::vector<double> part(nblk * ntheta);
@@ -695,9 +742,9 @@ static int ensure_small(b200bo_gp* gp) {
     int rc;
     if ((rc = gp->s_unit.reserve(sizeof(int2) * units.size()))) return rc;
     if ((rc = gp->s_rb.reserve(sizeof(int2) * rbs.size()))) return rc;
-    if ((rc = gp->s_ksm.reserve(sizeof(double) * (size_t)np * SMC))) return rc;
-    if ((rc = gp->s_partial.reserve(sizeof(double) * units.size() * SROWS * SMC))) return rc;
-    if ((rc = gp->s_mupart.reserve(sizeof(double) * (size_t)(np / 128) * SMC))) return rc;
+    if ((rc = gp->s_ksm.reserve(sizeof(double) * (size_t)SMAXP * np * SMC))) return rc;
+    if ((rc = gp->s_partial.reserve(sizeof(double) * (size_t)SMAXP * units.size() * SROWS * SMC))) return rc;
+    if ((rc = gp->s_mupart.reserve(sizeof(double) * (size_t)SMAXP * (np / 128) * SMC))) return rc;
     CU(cudaMemcpy(gp->s_unit.p, units.data(), sizeof(int2) * units.size(), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(gp->s_rb.p, rbs.data(), sizeof(int2) * rbs.size(), cudaMemcpyHostToDevice));
     gp->s_np = np;
@@ -731,6 +778,15 @@ static int predict_impl(int precision) {
     if (e && (e[0] == 't' || e[0] == 'T')) return PREDICT_IMPL_TF32;  // "tf32": fp32 mode on tcgen05
     if (e && (e[0] == 'd' || e[0] == 'D')) return PREDICT_IMPL_DMMA;
     return precision == B200BO_PRECISION_FP32 ? PREDICT_IMPL_TF32 : PREDICT_IMPL_DMMA;
+}
+
+// 8-warp (predict_acq_kernel) or 16-warp (predict_acq16_kernel) version of the fp64 kernel;
+// B200BO_PREDICT_WARPS=8|16 overrides the default for A/B measurements
+static int predict_warps() {
+    const char* e = getenv("B200BO_PREDICT_WARPS");
+    if (e && e[0] == '1' && e[1] == '6') return 16;
+    if (e && e[0] == '8') return 8;
+    return kDefaultPredictWarps;
 }
 
 // fp32 mode operand images of L^-1 (once per fit)
@@ -870,18 +926,21 @@ static int eval_core(const b200bo_acq* spec, const CandSrc& src, int64_t m, doub
             S.sg[g].mu_part = gp->s_mupart.as<double>();
             S.sg[g].unit_tab = gp->s_unit.as<int2>();
             S.sg[g].rb_tab = gp->s_rb.as<int2>();
+            S.nunits[g] = gp->s_nunits;
         }
+        S.m_end = m;
         CU(cudaEventRecord(g0->ev0, stream));
-        for (long long c0 = 0; c0 < m; c0 += SMC) {
+        for (long long c0 = 0; c0 < m; c0 += (long long)SMAXP * SMC) {
             S.c0 = c0;
-            S.mc = (int)((m - c0) < SMC ? (m - c0) : SMC);
+            const long long left = m - c0;
+            const int npass = (int)((left + SMC - 1) / SMC < SMAXP ? (left + SMC - 1) / SMC : SMAXP);
             for (int g = 0; g < spec->n_gps; ++g) {
-                small_kstar_kernel<<<spec->gps[g]->np / 128, 128, 0, stream>>>(S, g);
-                small_trsv_kernel<<<spec->gps[g]->s_nunits, 256, 0, stream>>>(S, g);
+                small_kstar_kernel<<<dim3(spec->gps[g]->np / 128, npass), 128, 0, stream>>>(S, g);
+                small_trsv_kernel<<<dim3(spec->gps[g]->s_nunits, npass), 256, 0, stream>>>(S, g);
                 LAUNCHED();
                 LAUNCHED();
             }
-            small_finish_kernel<<<1, 1024, 0, stream>>>(S);
+            small_finish_kernel<<<npass, 1024, 0, stream>>>(S);
             LAUNCHED();
         }
         CU(cudaGetLastError());
@@ -919,6 +978,11 @@ static int eval_core(const b200bo_acq* spec, const CandSrc& src, int64_t m, doub
             } else {
                 predict_acq_tc_kernel<false><<<grid, PNT, kPredictSmemBytesTc, stream>>>(P);
             }
+        } else if (predict_impl(g0->precision) == PREDICT_IMPL_DMMA && predict_warps() == 16) {
+            if (dreg)
+                predict_acq16_kernel<true><<<grid, P16_NT, kPredictSmemBytesDmma, stream>>>(P);
+            else
+                predict_acq16_kernel<false><<<grid, P16_NT, kPredictSmemBytesDmma, stream>>>(P);
         } else if (predict_impl(g0->precision) == PREDICT_IMPL_DMMA) {
             if (dreg)
                 predict_acq_kernel<PREDICT_IMPL_DMMA, true><<<grid, PNT, kPredictSmemBytesDmma, stream>>>(P);

@@ -31,12 +31,18 @@ __global__ void scale_x_kernel(const double* __restrict__ X, const double* __res
 // K(X,X): full symmetric np x np matrix; K_ii = const + alpha; padding = identity.
 // (SK/gaussian_process/kernels.py:1716,1740-1743 + _gpr.py:350)
 // ---------------------------------------------------------------------------------------
-// 32x32 output tile per CTA (32x8 threads, 4 rows each); the two 32-row slabs of Xs are staged in
-// shared memory with coalesced loads (row stride 65: conflict-free when lanes walk different rows).
+// 32x32 output tile per CTA (32x8 threads, 4 rows each); only tiles on or below the diagonal are computed
+// (K is symmetric: pdist evaluates each pair once, kernels.py:1740-1743) and written twice - directly and,
+// through a shared-memory transpose, mirrored - so every global store is a coalesced 256-byte row segment.
+// The two 32-row slabs of Xs are staged in shared memory (row stride 65: conflict-free when lanes walk
+// different rows).  COV is a template parameter: straight-line covariance code as in the predict kernel.
+template <int COV>
 __global__ void __launch_bounds__(256)
-kbuild_kernel(const double* __restrict__ Xs, double* __restrict__ K, int n, int np, int d, int family,
-              int nu, double constv, double jitter) {
+kbuild_kernel(const double* __restrict__ Xs, double* __restrict__ K, int n, int np, int d, double constv,
+              double jitter) {
+    if (blockIdx.x > blockIdx.y) return;  // strictly-upper tiles are produced by their mirror
     __shared__ double xi[32][B200BO_MAX_DIM + 1], xj[32][B200BO_MAX_DIM + 1];
+    __shared__ double tile[32][33];
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
     const int j0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
     for (int idx = tid; idx < 32 * d; idx += 256) {
@@ -54,16 +60,23 @@ kbuild_kernel(const double* __restrict__ Xs, double* __restrict__ K, int n, int 
         } else if (i == j) {
             v = constv + jitter;
         } else {
-            // (a-b)^2 is symmetric, so K is too (pdist evaluates each pair once)
+            // the difference is formed as (row with the larger index) - (the other): identical bits on both
+            // sides of the diagonal whichever tile produces the pair
             double r2 = 0.0;
+            const double* a = (i > j) ? xi[rr] : xj[tx];
+            const double* b = (i > j) ? xj[tx] : xi[rr];
             for (int t = 0; t < d; ++t) {
-                const double df = xi[rr][t] - xj[tx][t];
+                const double df = a[t] - b[t];
                 r2 += df * df;
             }
-            v = constv * cov_from_r2(r2, family, nu);
+            v = constv * cov_eval<COV>(r2);
         }
         K[(size_t)i * np + j] = v;
+        tile[rr][tx] = v;
     }
+    if (blockIdx.x == blockIdx.y) return;
+    __syncthreads();
+    for (int rr = ty; rr < 32; rr += 8) K[(size_t)(j0 + rr) * np + i0 + tx] = tile[tx][rr];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -156,6 +169,141 @@ dgemm64_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, 
                 const double v = alpha * acc[i][j][e];
                 *c = (beta == 0.0) ? v : fma(beta, *c, v);
             }
+}
+
+// ---------------------------------------------------------------------------------------
+// fp64 GEMM on 128x128 tiles: the workhorse of the fit side (trailing SYRK/GEMM updates of the blocked
+// Cholesky, the triangular-inverse recursion, K^-1 = W^T W, predict(return_cov)).  Same contract as
+// dgemm64_kernel (opA/opB, lower_only, kmode, batching) with M, N arbitrary multiples of 64 (edge tiles are
+// predicated) and K a multiple of 16.  256 threads, warp tile 32(m) x 64(n), mma.sync m8n8k4 f64 (DMMA),
+// k-tile 16, 3-stage 16-byte cp.async pipeline with the prefetch issued behind the first MMA batch - the
+// machinery of predict_phase_b_dmma.  Each operand keeps in shared memory the orientation it has in global
+// memory (so that every copy is a straight 16-byte cp.async):
+//   k-major  [16][132]  (stride 264 words = 8 mod 32)   for A^T-stored / B-stored operands
+//   mn-major [128][20]  (stride 40 words = 8 mod 32)    for A-stored / B^T-stored operands
+// both give conflict-free LDS.64 fragment loads (an LDS.64 is served per half-warp: 4 k x 4 m).
+// ---------------------------------------------------------------------------------------
+constexpr int G128_BK = 16, G128_STAGES = 3;
+constexpr int G128_KSTR = 132, G128_MSTR = 20;
+constexpr int G128_OPER = 128 * G128_MSTR;  // doubles per operand per stage (>= 16 * 132)
+constexpr int kGemm128SmemBytes = G128_STAGES * 2 * G128_OPER * 8;  // 122880
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool valid) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(bytes));
+}
+
+// one operand tile: 128 (m or n) x 16 (k).  TRANS = stored [k][mn] in global (contiguous in mn).
+template <bool TRANS>
+__device__ __forceinline__ void g128_load_operand(double* sm, const double* __restrict__ G, int ld, int mn0,
+                                                  int k0, int mn_limit) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int q = tid + t * 256;
+        if (TRANS) {
+            const int kk = q >> 6, c = (q & 63) * 2;
+            const bool ok = mn0 + c < mn_limit;
+            cp_async16_zfill(sm + kk * G128_KSTR + c, G + (size_t)(k0 + kk) * ld + (ok ? mn0 + c : 0), ok);
+        } else {
+            const int r = q >> 3, c = (q & 7) * 2;
+            const bool ok = mn0 + r < mn_limit;
+            cp_async16_zfill(sm + r * G128_MSTR + c, G + (size_t)(ok ? mn0 + r : 0) * ld + k0 + c, ok);
+        }
+    }
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256, 1)
+dgemm128_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int lda, long long sA,
+                const double* __restrict__ B, int ldb, long long sB, double beta, double* C, int ldc,
+                long long sC, int lower_only, int kmode) {
+    extern __shared__ __align__(16) double g128_smem[];
+    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
+    if (lower_only && n0 > m0) return;
+    A += (long long)blockIdx.z * sA;
+    B += (long long)blockIdx.z * sB;
+    C += (long long)blockIdx.z * sC;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int g = lane >> 2, t4 = lane & 3;
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    int kbeg = 0, kend = K;
+    if (kmode == 1) kend = min(K, m0 + 128);
+    if (kmode == 2) kbeg = n0;
+    if (kmode == 3) kbeg = max(m0, n0);
+    const int nks = (kend - kbeg) / G128_BK;
+    auto stage_a = [&](int s) { return g128_smem + (size_t)s * 2 * G128_OPER; };
+    auto stage_b = [&](int s) { return g128_smem + (size_t)s * 2 * G128_OPER + G128_OPER; };
+    auto load = [&](int s, int ks) {
+        const int k0 = kbeg + ks * G128_BK;
+        g128_load_operand<TA>(stage_a(s), A, lda, m0, k0, M);    // TA: A stored [k][m]
+        g128_load_operand<!TB>(stage_b(s), B, ldb, n0, k0, N);   // !TB: B stored [k][n]
+    };
+#pragma unroll
+    for (int s = 0; s < G128_STAGES - 1; ++s) {
+        if (s < nks) load(s, s);
+        cp_async_commit();
+    }
+    for (int ks = 0; ks < nks; ++ks) {
+        cp_async_wait<G128_STAGES - 2>();
+        __syncthreads();
+        const int nxt = ks + G128_STAGES - 1;
+        const double* as = stage_a(ks % G128_STAGES);
+        const double* bs = stage_b(ks % G128_STAGES);
+#pragma unroll
+        for (int k4 = 0; k4 < G128_BK / 4; ++k4) {
+            if (k4 == 1) {
+                if (nxt < nks) load(nxt % G128_STAGES, nxt);
+                cp_async_commit();
+            }
+            double a[4], b[8];
+            const int kk = k4 * 4 + t4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m = wm * 32 + i * 8 + g;
+                a[i] = TA ? as[kk * G128_KSTR + m] : as[m * G128_MSTR + kk];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = wn * 64 + j * 8 + g;
+                b[j] = TB ? bs[n * G128_MSTR + kk] : bs[kk * G128_KSTR + n];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                                 : "d"(a[i]), "d"(b[j]));
+        }
+    }
+    cp_async_wait<0>();
+    // C fragment: row = g, columns 2*t4 + {0,1}: one 16-byte store per fragment
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + wm * 32 + i * 8 + g;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = n0 + wn * 64 + j * 8 + 2 * t4;
+            if (n >= N) continue;
+            double2* c = reinterpret_cast<double2*>(C + (size_t)m * ldc + n);
+            double2 v = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
+            if (beta != 0.0) {
+                const double2 o = *c;
+                v.x = fma(beta, o.x, v.x);
+                v.y = fma(beta, o.y, v.y);
+            }
+            *c = v;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -491,6 +639,120 @@ __global__ void append_winv_kernel(double* __restrict__ W, double* __restrict__ 
 }
 
 constexpr int kMaxTheta = B200BO_MAX_DIM + 1;
+
+// gradient factor such that dk/dlog(l_t) = gcommon * D_t  (D_t = scaled squared difference)
+// (SK/gaussian_process/kernels.py:1761-1782 Matern, :1561-1573 RBF)
+template <int COV>
+__device__ __forceinline__ void cov_and_gradfactor(double r2, double& kval, double& gcommon) {
+    if (COV == 3) {
+        kval = exp_neg(0.5 * r2);
+        gcommon = kval;  // K_gradient = D * K
+    } else if (COV == 2) {
+        const double tmp = sqrt_pos(5.0 * r2);
+        const double e = exp_neg(tmp);
+        kval = (1.0 + tmp + tmp * tmp / 3.0) * e;
+        gcommon = 5.0 / 3.0 * (tmp + 1.0) * e;
+    } else if (COV == 1) {
+        const double tmp = sqrt_pos(3.0 * r2);
+        const double e = exp_neg(tmp);
+        kval = (1.0 + tmp) * e;
+        gcommon = 3.0 * e;
+    } else {  // nu = 0.5: K * D / sqrt(sum D), 0 where the distance is 0
+        const double den = sqrt(r2);
+        kval = exp_neg(den);
+        gcommon = (den != 0.0) ? kval / den : 0.0;
+    }
+}
+
+// Tiled version for d <= LG_DMAX: one CTA per 64x64 patch on or below the diagonal (K^-1 and dK/dtheta are
+// symmetric: pairs i > j count twice), each thread 16 pairs, per-theta sums kept in registers, ONE fixed-order
+// block reduction per theta at the end.  part[patch][p]; the host adds the patches in index order.
+constexpr int LG_DMAX = 16;
+template <int COV, bool ANISO>
+__global__ void __launch_bounds__(256)
+lml_grad_tile_kernel(const double* __restrict__ Xs, const double* __restrict__ Kinv, int ldk,
+                     const double* __restrict__ alphav, int n, int d, double constv, int has_const,
+                     double* __restrict__ part, int ntheta) {
+    const int bj = blockIdx.x, bi = blockIdx.y;
+    if (bj > bi) return;
+    // patch id in row-major order over the lower block triangle
+    const int bid = bi * (bi + 1) / 2 + bj;
+    __shared__ double xi[64][LG_DMAX + 1], xj[64][LG_DMAX + 1];
+    __shared__ double ai[64], aj[64];
+    __shared__ double red[8][LG_DMAX + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i0 = bi * 64, j0 = bj * 64;
+    for (int idx = tid; idx < 64 * d; idx += 256) {
+        const int r = idx / d, t = idx - r * d;
+        xi[r][t] = (i0 + r < n) ? Xs[(size_t)(i0 + r) * d + t] : 0.0;
+        xj[r][t] = (j0 + r < n) ? Xs[(size_t)(j0 + r) * d + t] : 0.0;
+    }
+    if (tid < 64) {
+        ai[tid] = (i0 + tid < n) ? alphav[i0 + tid] : 0.0;
+        aj[tid] = (j0 + tid < n) ? alphav[j0 + tid] : 0.0;
+    }
+    __syncthreads();
+    double acc_c = 0.0;
+    double acc[ANISO ? LG_DMAX : 1];
+#pragma unroll
+    for (int t = 0; t < (ANISO ? LG_DMAX : 1); ++t) acc[t] = 0.0;
+    const int cj = tid & 63;         // column of the patch (coalesced Kinv reads)
+    const int r0 = (tid >> 6) * 16;  // 16 consecutive rows
+    const int j = j0 + cj;
+    for (int rr = 0; rr < 16; ++rr) {
+        const int ri = r0 + rr, i = i0 + ri;
+        if (i >= n || j >= n || j > i) continue;
+        double w = ai[ri] * aj[cj] - Kinv[(size_t)i * ldk + j];
+        if (i != j) w *= 2.0;
+        double r2 = 0.0;
+        double df2[ANISO ? LG_DMAX : 1];
+#pragma unroll
+        for (int t = 0; t < LG_DMAX; ++t) {
+            if (t < d) {
+                const double df = xi[ri][t] - xj[cj][t];
+                const double q = df * df;
+                r2 += q;
+                if (ANISO) df2[t] = q;
+            }
+        }
+        double kval, gcommon;
+        cov_and_gradfactor<COV>(r2, kval, gcommon);
+        if (i == j) kval = 1.0;
+        acc_c = fma(w, constv * kval, acc_c);
+        const double base = w * constv * gcommon;
+        if (ANISO) {
+#pragma unroll
+            for (int t = 0; t < LG_DMAX; ++t)
+                if (t < d) acc[t] = fma(base, df2[t], acc[t]);
+        } else {
+            acc[0] = fma(base, r2, acc[0]);
+        }
+    }
+    // fixed-order reduction: lanes (butterfly), then the 8 warps in index order
+    const int nls = ANISO ? d : 1;
+    for (int q = 0; q <= nls; ++q) {
+        double v = (q == 0) ? acc_c : 0.0;
+        if (q > 0) {
+#pragma unroll
+            for (int t = 0; t < (ANISO ? LG_DMAX : 1); ++t)
+                if (t == q - 1) v = acc[t];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][q] = v;
+    }
+    __syncthreads();
+    if (tid <= nls) {
+        double s = 0.0;
+        for (int w8 = 0; w8 < 8; ++w8) s += red[w8][tid];
+        // theta order: [log const (if has_const)], log length_scale...
+        if (tid == 0) {
+            if (has_const) part[(size_t)bid * ntheta] = 0.5 * s;
+        } else {
+            part[(size_t)bid * ntheta + (has_const ? 1 : 0) + tid - 1] = 0.5 * s;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256)
 lml_grad_kernel(const double* __restrict__ Xs, const double* __restrict__ Kinv, int ldk,

@@ -1086,12 +1086,24 @@ struct SmallGp {
     const int2* rb_tab;     // [np/SROWS] (first unit, number of units)
 };
 
+// One launch group covers up to SMAXP passes (blockIdx.y / blockIdx.x of the finish kernel = pass): the
+// passes of a batch run concurrently (an L-BFGS-B round of all seeds + their stencils is ~170 rows = 6
+// passes: 3 launches instead of 18, and six times as many CTAs in flight).
+constexpr int SMAXP = 8;
+
 struct SmallParams {
     PredictParams P;
     SmallGp sg[B200BO_MAX_GPS];
-    long long c0;  // first candidate of this pass
-    int mc;        // candidates in this pass (<= SMC)
+    long long c0;  // first candidate of pass 0 of this launch group
+    long long m_end;  // one past the last candidate of the batch
+    int nunits[B200BO_MAX_GPS];  // work units per pass (stride of `partial` between passes)
 };
+
+__device__ __forceinline__ long long small_pass_c0(const SmallParams& S, int pass) { return S.c0 + (long long)pass * SMC; }
+__device__ __forceinline__ int small_pass_mc(const SmallParams& S, int pass) {
+    const long long left = S.m_end - small_pass_c0(S, pass);
+    return (int)(left < SMC ? (left < 0 ? 0 : left) : SMC);
+}
 
 __global__ void __launch_bounds__(128)
 small_kstar_kernel(const SmallParams S, int g) {
@@ -1100,11 +1112,15 @@ small_kstar_kernel(const SmallParams S, int g) {
     __shared__ double xc_s[SMC * B200BO_MAX_DIM];
     __shared__ double wsum[4][SMC];
     const int tid = threadIdx.x, d = S.P.d;
+    const int pass = blockIdx.y, mc = small_pass_mc(S, pass);
+    const long long pc0 = small_pass_c0(S, pass);
+    double* ksm = Q.ksm + (size_t)pass * G.np * SMC;
+    double* mu_part = Q.mu_part + (size_t)pass * (G.np / 128) * SMC;
     for (int idx = tid; idx < SMC * d; idx += 128) {
         const int c = idx / d, j = idx - c * d;
         double v = 0.0;
-        if (c < S.mc) {
-            v = candidate_coord(S.P, S.c0 + c, j);
+        if (c < mc) {
+            v = candidate_coord(S.P, pc0 + c, j);
             if (G.xform && G.xform[j] == B200BO_XFORM_ROUND) v = rint(v);
             v = v / G.ls[j];
         }
@@ -1116,7 +1132,7 @@ small_kstar_kernel(const SmallParams S, int g) {
     const double an = G.alphav[n];
     for (int c = 0; c < SMC; ++c) {
         double kv = 0.0;
-        if (c < S.mc && n < G.n) {
+        if (c < mc && n < G.n) {
             double r2 = 0.0;
             for (int j = 0; j < d; ++j) {
                 const double df = xc_s[c * d + j] - xr[j];
@@ -1124,7 +1140,7 @@ small_kstar_kernel(const SmallParams S, int g) {
             }
             kv = G.constv * cov_from_r2(r2, G.family, G.nu);
         }
-        Q.ksm[(size_t)n * SMC + c] = kv;
+        ksm[(size_t)n * SMC + c] = kv;
         double t = an * kv;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
@@ -1132,7 +1148,7 @@ small_kstar_kernel(const SmallParams S, int g) {
     }
     __syncthreads();
     if (tid < SMC)
-        Q.mu_part[(size_t)blockIdx.x * SMC + tid] = ((wsum[0][tid] + wsum[1][tid]) + wsum[2][tid]) + wsum[3][tid];
+        mu_part[(size_t)blockIdx.x * SMC + tid] = ((wsum[0][tid] + wsum[1][tid]) + wsum[2][tid]) + wsum[3][tid];
 }
 
 __global__ void __launch_bounds__(256)
@@ -1142,6 +1158,8 @@ small_trsv_kernel(const SmallParams S, int g) {
     __shared__ __align__(16) double Wt[SROWS * SWSTR];
     __shared__ __align__(16) double Kt[SKT * SMC];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pass = blockIdx.y;
+    const double* ksm = Q.ksm + (size_t)pass * G.np * SMC;
     const int2 u = Q.unit_tab[blockIdx.x];
     const int r0 = u.x * SROWS;
     const int kbeg = u.y * SKCH;
@@ -1155,7 +1173,7 @@ small_trsv_kernel(const SmallParams S, int g) {
             const int r = idx / SKT, kk = idx % SKT;
             Wt[r * SWSTR + kk] = Q.W[(size_t)(r0 + r) * np + k0 + kk];
         }
-        for (int idx = tid; idx < SKT * SMC; idx += 256) Kt[idx] = Q.ksm[(size_t)k0 * SMC + idx];
+        for (int idx = tid; idx < SKT * SMC; idx += 256) Kt[idx] = ksm[(size_t)k0 * SMC + idx];
         __syncthreads();
 #pragma unroll 4
         for (int kk = 0; kk < SKT; kk += 2) {
@@ -1169,7 +1187,7 @@ small_trsv_kernel(const SmallParams S, int g) {
         }
         __syncthreads();
     }
-    double* out = Q.partial + (size_t)blockIdx.x * SROWS * SMC;
+    double* out = Q.partial + ((size_t)pass * S.nunits[g] + blockIdx.x) * SROWS * SMC;
 #pragma unroll
     for (int q = 0; q < 8; ++q) out[(warp * 8 + q) * SMC + lane] = acc[q];
 }
@@ -1180,15 +1198,19 @@ small_finish_kernel(const SmallParams S) {
     __shared__ double colsq_s[B200BO_MAX_GPS][SMC];
     __shared__ double mu_s[B200BO_MAX_GPS][SMC];
     const int tid = threadIdx.x, c = tid & 31, rg = tid >> 5;
+    const int pass = blockIdx.x, mc = small_pass_mc(S, pass);
+    const long long pc0 = small_pass_c0(S, pass);
     for (int g = 0; g < S.P.n_gps; ++g) {
         const GpDev& G = S.P.gp[g];
         const SmallGp& Q = S.sg[g];
+        const double* partial = Q.partial + (size_t)pass * S.nunits[g] * SROWS * SMC;
+        const double* mu_part = Q.mu_part + (size_t)pass * (G.np / 128) * SMC;
         double s = 0.0;
         for (int row = rg; row < G.np; row += 32) {
             const int2 rb = Q.rb_tab[row / SROWS];
             const int r = row % SROWS;
             double v = 0.0;
-            for (int j = 0; j < rb.y; ++j) v += Q.partial[((size_t)(rb.x + j) * SROWS + r) * SMC + c];
+            for (int j = 0; j < rb.y; ++j) v += partial[((size_t)(rb.x + j) * SROWS + r) * SMC + c];
             s = fma(v, v, s);
         }
         red[rg][c] = s;
@@ -1199,15 +1221,15 @@ small_finish_kernel(const SmallParams S) {
             colsq_s[g][c] = t;
             double m = 0.0;
             const int nb = G.np / 128;
-            for (int b = 0; b < nb; ++b) m += Q.mu_part[(size_t)b * SMC + c];
+            for (int b = 0; b < nb; ++b) m += mu_part[(size_t)b * SMC + c];
             mu_s[g][c] = m;
         }
         __syncthreads();
     }
-    if (rg == 0 && c < S.mc) {
+    if (rg == 0 && c < mc) {
         double base_neg = 0.0, prod = 1.0;
         for (int g = 0; g < S.P.n_gps; ++g)
-            candidate_epilogue(S.P, S.P.gp[g], g, mu_s[g][c], colsq_s[g][c], S.c0 + c, base_neg, prod);
+            candidate_epilogue(S.P, S.P.gp[g], g, mu_s[g][c], colsq_s[g][c], pc0 + c, base_neg, prod);
     }
 }
 

@@ -9,15 +9,18 @@ import warnings
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))  # the vendored, unmodified reference (tools/vendor_ref.py)
 import bayesianoptimization_b200 as bo  # noqa: E402
+from bayes_opt.target_space import TargetSpace  # noqa: E402
 from sklearn.gaussian_process.kernels import Matern  # noqa: E402
 
 warnings.simplefilter("ignore")
 out = {}
 for n, d in [(1024, 8), (4096, 16)]:
     rs = np.random.RandomState(0)
-    space = bo.TargetSpace(None, {f"x{i:02d}": (0.0, 1.0) for i in range(d)})
+    space = TargetSpace(None, {f"x{i:02d}": (0.0, 1.0) for i in range(d)})
     X = space.random_sample(n, rs)
     y = np.sin(X.sum(1)) + 0.1 * np.random.RandomState(0).randn(n)
     space._params, space._target = X, y
@@ -91,7 +94,7 @@ def black_box(x, y):
     return -(x**2) - (y - 1) ** 2 + 1
 
 
-space = bo.TargetSpace(black_box, {"x": (2, 4), "y": (-3, 3)})
+space = TargetSpace(black_box, {"x": (2, 4), "y": (-3, 3)})
 rs = np.random.RandomState(1)
 for _ in range(25):
     space.probe(space.random_sample(random_state=rs))
