@@ -111,6 +111,10 @@ struct b200bo_gp {
     DevBuf sel_cta;         // per-CTA running selection lists of the fused kernels
     DevBuf pbounds, prow;   // throughput mode: Philox bounds (lo, span) / regenerated winner rows
     bool replica = false;   // predict-only copy made by b200bo_gp_replicate
+    // look-ahead Cholesky: bulk stream, chain/bulk events, copy of the next diagonal step's panel block
+    cudaStream_t bulk_stream = nullptr;
+    cudaEvent_t ev_chain = nullptr, ev_bulk = nullptr;
+    DevBuf pside;
     // streamed host batches: copy / execute streams and the double-buffer events
     cudaStream_t copy_stream = nullptr, exec_stream = nullptr;
     cudaEvent_t chunk_up[2] = {nullptr, nullptr}, chunk_done[2] = {nullptr, nullptr};
@@ -228,9 +232,12 @@ extern "C" void b200bo_gp_destroy(b200bo_gp* gp) {
                       &gp->pscratch, &gp->xc, &gp->out_acq, &gp->out_mu, &gp->out_sd, &gp->sel,
                       &gp->clamp, &gp->s_ksm, &gp->s_partial, &gp->s_mupart, &gp->s_unit, &gp->s_rb,
                       &gp->tc_linv, &gp->cov_xc, &gp->cov_kst, &gp->cov_v, &gp->cov_c, &gp->cov_out, &gp->cov_mu,
-                      &gp->sel_cta, &gp->pbounds, &gp->prow};
+                      &gp->sel_cta, &gp->pbounds, &gp->prow, &gp->pside};
     for (DevBuf* b : bufs) b->release();
     if (gp->stream) cudaStreamDestroy(gp->stream);
+    if (gp->bulk_stream) cudaStreamDestroy(gp->bulk_stream);
+    if (gp->ev_chain) cudaEventDestroy(gp->ev_chain);
+    if (gp->ev_bulk) cudaEventDestroy(gp->ev_bulk);
     if (gp->copy_stream) cudaStreamDestroy(gp->copy_stream);
     if (gp->exec_stream) cudaStreamDestroy(gp->exec_stream);
     for (int i = 0; i < 2; ++i) {
@@ -362,21 +369,31 @@ static int check_kernel(const b200bo_gp* gp, const b200bo_kernel* k) {
     return B200BO_OK;
 }
 
+static int ensure_bulk_stream(b200bo_gp* gp) {
+    if (!gp->bulk_stream) {
+        CU(cudaStreamCreateWithFlags(&gp->bulk_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&gp->ev_chain, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&gp->ev_bulk, cudaEventDisableTiming));
+    }
+    return B200BO_OK;
+}
+
 template <bool TA, bool TB>
 static int gemm(int M, int N, int K, double alpha, const double* A, int lda, long long sA,
                 const double* B, int ldb, long long sB, double beta, double* C, int ldc,
-                long long sC, int batch, int lower_only, int kmode) {
+                long long sC, int batch, int lower_only, int kmode, int skip = 0, const cudaStream_t* stp = nullptr) {
     if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return B200BO_OK;
+    const cudaStream_t st = stp ? *stp : g_st;
     // 128x128 pipelined tiles wherever a tile can be filled; the 64x64 kernel for narrow panels / small blocks
     static const bool force64 = [] { const char* e = getenv("B200BO_GEMM"); return e && e[0] == '6'; }();
     if (M >= 128 && N >= 128 && !force64) {
         dim3 grid((N + 127) / 128, (M + 127) / 128, batch);
-        dgemm128_kernel<TA, TB><<<grid, 256, kGemm128SmemBytes, g_st>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta,
-                                                                        C, ldc, sC, lower_only, kmode);
+        dgemm128_kernel<TA, TB><<<grid, 256, kGemm128SmemBytes, st>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta,
+                                                                      C, ldc, sC, lower_only, kmode, skip);
     } else {
         dim3 grid(N / 64, M / 64, batch);
-        dgemm64_kernel<TA, TB><<<grid, 256, 0, g_st>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC,
-                                                       lower_only, kmode);
+        dgemm64_kernel<TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC,
+                                                     lower_only, kmode, skip);
     }
     LAUNCHED();
     CU(cudaGetLastError());
@@ -418,29 +435,73 @@ static int factorize(b200bo_gp* gp, const b200bo_kernel* kern, double jitter, in
     CU(cudaMemsetAsync(W, 0, sizeof(double) * (size_t)np * np, g_st));
     CU(cudaMemsetAsync(gp->info.p, 0, sizeof(int), g_st));
     // right-looking blocked Cholesky, panel width 64.  B200BO_POTRF=legacy selects the first
-    // (unblocked) diagonal-block kernel for A/B measurements; the factor is bit-identical.
+    // (unblocked) diagonal-block kernel, B200BO_POTRF=serial the blocked kernel without look-ahead, for A/B
+    // measurements.
     const char* pv = getenv("B200BO_POTRF");
     const bool legacy_potrf = pv && (pv[0] == 'l' || pv[0] == 'L');
-    for (int j0 = 0; j0 < np; j0 += 64) {
-        if (legacy_potrf)
-            potrf_diag_legacy_kernel<<<1, 256, kPotrfLegacySmemBytes, g_st>>>(L, np, j0, W + (size_t)j0 * np + j0, np,
-                                                                        gp->info.as<int>());
-        else
-            potrf_diag_kernel<<<1, 256, kPotrfSmemBytes, g_st>>>(L, np, j0, W + (size_t)j0 * np + j0, np,
-                                                           gp->info.as<int>());
+    const bool serial_potrf = pv && (pv[0] == 's' || pv[0] == 'S');
+    if (legacy_potrf || serial_potrf || np <= 128) {
+        for (int j0 = 0; j0 < np; j0 += 64) {
+            if (legacy_potrf)
+                potrf_diag_legacy_kernel<<<1, 256, kPotrfLegacySmemBytes, g_st>>>(L, np, j0, W + (size_t)j0 * np + j0, np,
+                                                                            gp->info.as<int>());
+            else
+                potrf_diag_kernel<<<1, 256, kPotrfSmemBytes, g_st>>>(L, np, j0, W + (size_t)j0 * np + j0, np,
+                                                               gp->info.as<int>(), nullptr, nullptr, 0);
+            LAUNCHED();
+            const int below = np - j0 - 64;
+            if (below > 0) {
+                double* panel = L + (size_t)(j0 + 64) * np + j0;
+                // L_ij = A_ij * inv(L_jj)^T
+                if ((rc = gemm<false, true>(below, 64, 64, 1.0, panel, np, 0, W + (size_t)j0 * np + j0, np, 0,
+                                            0.0, panel, np, 0, 1, 0, 0)))
+                    return rc;
+                // trailing update (lower tiles only): A_ik -= L_ij L_kj^T
+                if ((rc = gemm<false, true>(below, below, 64, -1.0, panel, np, 0, panel, np, 0, 1.0,
+                                            L + (size_t)(j0 + 64) * np + j0 + 64, np, 0, 1, 1, 0)))
+                    return rc;
+            }
+        }
+    } else {
+        // Look-ahead: the 64 diagonal blocks are a dependent chain of single-CTA kernels; everything else of a
+        // step (panel solve, trailing update) is bulk work for the whole GPU.  The chain runs on the handle's
+        // stream, the bulk on a second stream; the diagonal kernel of step j+1 resolves its dependence on
+        // panel j itself (potrf_diag_kernel, look-ahead form) from a copy of A[j+1, j] taken before the bulk
+        // panel solve, and the bulk trailing update leaves block (j+1, j+1) alone.  Every value is produced by
+        // exactly one kernel: the result does not depend on how the two streams interleave.
+        int rc2;
+        if ((rc2 = ensure_bulk_stream(gp))) return rc2;
+        const cudaStream_t sb = gp->bulk_stream;
+        if ((rc = gp->pside.reserve(sizeof(double) * 64 * 64))) return rc;
+        double* Pside = gp->pside.as<double>();
+        CU(cudaEventRecord(gp->ev_chain, g_st));
+        CU(cudaStreamWaitEvent(sb, gp->ev_chain, 0));  // K build / copies issued so far
+        potrf_diag_kernel<<<1, 256, kPotrfSmemBytes, g_st>>>(L, np, 0, W, np, gp->info.as<int>(), nullptr, nullptr, 0);
         LAUNCHED();
-        const int below = np - j0 - 64;
-        if (below > 0) {
-            double* panel = L + (size_t)(j0 + 64) * np + j0;
-            // L_ij = A_ij * inv(L_jj)^T
-            if ((rc = gemm<false, true>(below, 64, 64, 1.0, panel, np, 0, W + (size_t)j0 * np + j0, np, 0,
-                                        0.0, panel, np, 0, 1, 0, 0)))
+        CU(cudaEventRecord(gp->ev_chain, g_st));
+        for (int j0 = 0; j0 + 64 < np; j0 += 64) {
+            const int below = np - j0 - 64;
+            double* panel = L + (size_t)(j0 + 64) * np + j0;  // rows below the diagonal block, columns of panel j
+            const double* Dj = W + (size_t)j0 * np + j0;
+            CU(cudaStreamWaitEvent(sb, gp->ev_chain, 0));  // inv(L_jj) is ready (and the chain is done with Pside)
+            copy_block64_kernel<<<1, 256, 0, sb>>>(panel, np, Pside);
+            LAUNCHED();
+            CU(cudaEventRecord(gp->ev_bulk, sb));
+            if ((rc = gemm<false, true>(below, 64, 64, 1.0, panel, np, 0, Dj, np, 0, 0.0, panel, np, 0, 1, 0, 0, 0, &sb)))
                 return rc;
-            // trailing update (lower tiles only): A_ik -= L_ij L_kj^T
+            // chain: diagonal block j+1 (its A[j+1, j+1] holds the updates of panels < j: the bulk stream has finished them)
+            CU(cudaStreamWaitEvent(g_st, gp->ev_bulk, 0));
+            potrf_diag_kernel<<<1, 256, kPotrfSmemBytes, g_st>>>(L, np, j0 + 64, W + (size_t)(j0 + 64) * np + j0 + 64, np,
+                                                           gp->info.as<int>(), Pside, Dj, np);
+            LAUNCHED();
+            CU(cudaEventRecord(gp->ev_chain, g_st));
+            // bulk: trailing update of panel j on everything but block (j+1, j+1)
             if ((rc = gemm<false, true>(below, below, 64, -1.0, panel, np, 0, panel, np, 0, 1.0,
-                                        L + (size_t)(j0 + 64) * np + j0 + 64, np, 0, 1, 1, 0)))
+                                        L + (size_t)(j0 + 64) * np + j0 + 64, np, 0, 1, 1, 0, 64, &sb)))
                 return rc;
         }
+        CU(cudaEventRecord(gp->ev_bulk, sb));
+        CU(cudaStreamWaitEvent(g_st, gp->ev_bulk, 0));
     }
     {
         dim3 blk(32, 8), grd((np + 31) / 32, (np + 7) / 8);

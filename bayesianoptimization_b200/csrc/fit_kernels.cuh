@@ -96,9 +96,10 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 dgemm64_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int lda,
                long long sA, const double* __restrict__ B, int ldb, long long sB, double beta,
-               double* C, int ldc, long long sC, int lower_only, int kmode) {
+               double* C, int ldc, long long sC, int lower_only, int kmode, int skip) {
     const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
     if (lower_only && n0 > m0) return;
+    if (m0 < skip && n0 < skip) return;  // leading skip x skip block of C is left untouched (look-ahead Cholesky)
     A += (long long)blockIdx.z * sA;
     B += (long long)blockIdx.z * sB;
     C += (long long)blockIdx.z * sC;
@@ -218,7 +219,7 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256, 1)
 dgemm128_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int lda, long long sA,
                 const double* __restrict__ B, int ldb, long long sB, double beta, double* C, int ldc,
-                long long sC, int lower_only, int kmode) {
+                long long sC, int lower_only, int kmode, int skip) {
     extern __shared__ __align__(16) double g128_smem[];
     const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
     if (lower_only && n0 > m0) return;
@@ -293,7 +294,7 @@ dgemm128_kernel(int M, int N, int K, double alpha, const double* __restrict__ A,
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int n = n0 + wn * 64 + j * 8 + 2 * t4;
-            if (n >= N) continue;
+            if (n >= N || (m < skip && n < skip)) continue;  // skip: see dgemm64_kernel
             double2* c = reinterpret_cast<double2*>(C + (size_t)m * ldc + n);
             double2 v = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
             if (beta != 0.0) {
@@ -316,8 +317,14 @@ dgemm128_kernel(int M, int N, int K, double alpha, const double* __restrict__ A,
 // SP/linalg/_decomp_cholesky.py:58 raises LinAlgError on it).
 // ---------------------------------------------------------------------------------------
 constexpr int kPotrfSmemBytes = 3 * potrf::kB * potrf::kLd * 8;
+// Look-ahead form (Pprev != nullptr): the block's dependence on the PREVIOUS panel is resolved inside this
+// kernel, so that the factorisation chain does not wait for the bulk TRSM / trailing update of that panel:
+//   X = Pprev * Dprev^T      (Pprev = A[j, j-1] before the panel solve, Dprev = inv(L_{j-1,j-1}), both 64x64)
+//   S = A[j, j] - X X^T      (A[j, j] carries the updates of panels <= j-2; the bulk update of panel j-1 skips it)
+// The bulk stream computes its own copy of L[j, j-1] for the final factor; X is used here only.
 __global__ void __launch_bounds__(256)
-potrf_diag_kernel(double* A, int ld, int j0, double* Dinv, int ldd, int* info) {
+potrf_diag_kernel(double* A, int ld, int j0, double* Dinv, int ldd, int* info, const double* __restrict__ Pprev,
+                  const double* __restrict__ Dprev, int ldp) {
     using namespace potrf;
     extern __shared__ __align__(16) double potrf_smem[];
     double* S = potrf_smem;
@@ -328,9 +335,39 @@ potrf_diag_kernel(double* A, int ld, int j0, double* Dinv, int ldd, int* info) {
     for (int idx = tid; idx < kB * kB; idx += kThreads) {
         const int r = idx >> 6, c = idx & 63;
         S[r * kLd + c] = A[(size_t)(j0 + r) * ld + j0 + c];
-        V[r * kLd + c] = 0.0;
+        V[r * kLd + c] = Pprev ? Pprev[r * kB + c] : 0.0;
+        if (Pprev) T[r * kLd + c] = (c <= r) ? Dprev[(size_t)r * ldp + c] : 0.0;
     }
     __syncthreads();
+    if (Pprev) {
+        const int c = tid & 63, r0 = (tid >> 6) * 16;
+        double xv[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) xv[q] = 0.0;
+        for (int k = 0; k <= c; ++k) {  // Dprev is lower triangular: D[c][k] = 0 for k > c
+            const double dck = T[c * kLd + k];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) xv[q] = fma(V[(r0 + q) * kLd + k], dck, xv[q]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 16; ++q) V[(r0 + q) * kLd + c] = xv[q];
+        __syncthreads();
+        double sv[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) sv[q] = 0.0;
+        for (int k = 0; k < kB; ++k) {
+            const double xck = V[c * kLd + k];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) sv[q] = fma(V[(r0 + q) * kLd + k], xck, sv[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            if (c <= r0 + q) S[(r0 + q) * kLd + c] -= sv[q];
+        __syncthreads();
+        for (int idx = tid; idx < kB * kB; idx += kThreads) V[(idx >> 6) * kLd + (idx & 63)] = 0.0;
+        __syncthreads();
+    }
     for (int c0 = 0; c0 < kB; c0 += kPw) {
         if (warp == 0) {
             const int bad = diag_factor(S, diag, rdiag, c0);
@@ -432,6 +469,12 @@ potrf_diag_legacy_kernel(double* A, int ld, int j0, double* Dinv, int ldd, int* 
         const int r = idx >> 6, c = idx & 63;
         Dinv[(size_t)r * ldd + c] = V[r][c];
     }
+}
+
+// dst[64][64] (dense) = src[64 rows][64 cols] with row stride ld: the look-ahead copy of A[j+1, j] taken
+// before the bulk stream's in-place panel solve overwrites it
+__global__ void __launch_bounds__(256) copy_block64_kernel(const double* __restrict__ src, int ld, double* __restrict__ dst) {
+    for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) dst[idx] = src[(size_t)(idx >> 6) * ld + (idx & 63)];
 }
 
 // zero the strict upper triangle (scipy.linalg.cholesky(lower=True) returns a clean factor)

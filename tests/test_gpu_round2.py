@@ -258,3 +258,64 @@ def test_lazy_lml_value_and_2d_validation(bo):
         gp.predict(X[0])
     with pytest.raises(ValueError):
         bo.B200GaussianProcessRegressor(kernel=Matern(nu=2.5), optimizer=None).fit(X[:, 0], y)
+
+
+@pytest.mark.parametrize("n,d", [(129, 3), (700, 5), (2048, 16), (4096, 16)])
+def test_lookahead_cholesky_and_tiled_gemm_vs_serial_and_sklearn(bo, monkeypatch, n, d):
+    """Fit side, round 2: look-ahead Cholesky (diagonal chain on one stream, panel solve + trailing update on a
+    second one, potrf_diag_kernel resolving the previous panel itself) with 128x128 pipelined DMMA tiles,
+    against (a) the serial loop on 64x64 tiles of round 1 (B200BO_POTRF=serial, B200BO_GEMM=64): same factor to
+    round-off, (b) itself: bit-identical on repetition (no race between the two streams), (c) LML + gradient of
+    sklearn."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+
+    from bayesianoptimization_b200 import _lib as B
+
+    X, y = _synth(n, d, 3)
+
+    def run():
+        gp = _gp(bo, X, y, ls=0.8)
+        W = np.empty((n, n))
+        B.check(B.lib().b200bo_gp_get(gp._handle().ptr, B.GET_LINV, B.as_dp(W), n * n))
+        lml, grad = gp.log_marginal_likelihood(np.log([0.6]), eval_gradient=True)
+        return gp.L_.copy(), W, gp.alpha_.copy(), lml, grad
+
+    a = run()
+    b = run()
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)  # deterministic whatever the stream interleaving
+    monkeypatch.setenv("B200BO_POTRF", "serial")
+    monkeypatch.setenv("B200BO_GEMM", "64")
+    c = run()
+    assert_allclose(a[0], c[0], rtol=1e-8, atol=1e-11)
+    assert np.all(np.triu(a[0], 1) == 0)
+    assert np.max(np.abs(a[1] @ a[0] - np.eye(n))) < 1e-6
+    assert_allclose(a[2], c[2], rtol=1e-6)
+    assert a[3] == pytest.approx(c[3], rel=1e-9) and a[4][0] == pytest.approx(c[4][0], rel=1e-6)
+    if n <= 2048:
+        sk = GaussianProcessRegressor(kernel=Matern(nu=2.5, length_scale=0.8), alpha=1e-6, normalize_y=True,
+                                      optimizer=None).fit(X, y)
+        l0, g0 = sk.log_marginal_likelihood(np.log([0.6]), eval_gradient=True)
+        assert a[3] == pytest.approx(l0, rel=1e-8) and a[4][0] == pytest.approx(g0[0], rel=1e-5, abs=1e-6)
+        assert_allclose(a[0], sk.L_, rtol=1e-7, atol=1e-10)
+
+
+@pytest.mark.parametrize("tag", ["aniso_const", "rbf_iso"])
+def test_tiled_lml_gradient_kernel_families(bo, tag):
+    """lml_grad_tile_kernel (templated covariance, iso/aniso, optional ConstantKernel) against sklearn."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel
+
+    X, y = _synth(300, 4, 8)
+    if tag == "aniso_const":
+        k = ConstantKernel(1.7) * Matern(nu=1.5, length_scale=[0.5, 0.9, 1.3, 0.7])
+        theta = np.log([2.0, 0.6, 0.8, 1.1, 0.9])
+    else:
+        k = RBF(length_scale=0.8)
+        theta = np.log([0.5])
+    gp = bo.B200GaussianProcessRegressor(kernel=k, alpha=1e-6, normalize_y=True, optimizer=None).fit(X, y)
+    sk = GaussianProcessRegressor(kernel=k, alpha=1e-6, normalize_y=True, optimizer=None).fit(X, y)
+    l1, g1 = gp.log_marginal_likelihood(theta, eval_gradient=True)
+    l0, g0 = sk.log_marginal_likelihood(theta, eval_gradient=True)
+    assert l1 == pytest.approx(l0, rel=1e-8)
+    assert_allclose(g1, g0, rtol=1e-5, atol=1e-6)

@@ -11,7 +11,7 @@ if [ "$mode" = "tests" ] || [ "$mode" = "all" ]; then
   rc=$?; echo "pytest exit $rc"; tail -n 60 $out/pytest_gpu.log
   if [ $rc -ne 0 ]; then
     echo "== pytest gpu, fit-side GEMMs on the 64x64 kernel (A/B)"
-    B200BO_GEMM=64 timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=line -p no:cacheprovider -x > $out/pytest_gpu_gemm64.log 2>&1
+    B200BO_GEMM=64 B200BO_POTRF=serial timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=line -p no:cacheprovider -x > $out/pytest_gpu_gemm64.log 2>&1
     echo "pytest(gemm64) exit $?"; tail -n 15 $out/pytest_gpu_gemm64.log
   fi
   echo "== smoke"
@@ -26,7 +26,7 @@ fi
 if [ "$mode" = "bench" ] || [ "$mode" = "all" ] || [ "$mode" = "fit" ]; then
   echo "== fit / suggest side bench"
   timeout 900 python tools/fit_bench.py > $out/fit_bench.json 2> $out/fit_bench.err; cat $out/fit_bench.json; tail -n 3 $out/fit_bench.err
-  B200BO_GEMM=64 timeout 900 python tools/fit_bench.py > $out/fit_bench_gemm64.json 2> $out/fit_bench_gemm64.err; cat $out/fit_bench_gemm64.json
+  B200BO_GEMM=64 B200BO_POTRF=serial timeout 900 python tools/fit_bench.py > $out/fit_bench_gemm64.json 2> $out/fit_bench_gemm64.err; cat $out/fit_bench_gemm64.json
 fi
 if [ "$mode" = "prof" ]; then
   echo "== ncu launch list"
