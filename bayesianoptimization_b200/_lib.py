@@ -37,7 +37,7 @@ class KernelSpec(C.Structure):
     _fields_ = [
         ("family", C.c_int32), ("nu", C.c_int32), ("n_length_scale", C.c_int32),
         ("reserved", C.c_int32), ("const_value", C.c_double),
-        ("length_scale", C.POINTER(C.c_double)),
+        ("length_scale", C.POINTER(C.c_double)), ("noise_level", C.c_double),
     ]
 
 

@@ -92,7 +92,8 @@ struct b200bo_gp {
     bool has_data = false, fitted = false;
     // kernel of the last fit
     int family = 0, nu = B200BO_NU_25;
-    double constv = 1.0, jitter = 0.0;
+    double constv = 1.0, jitter = 0.0;  // jitter = alpha + WhiteKernel noise_level (diagonal of K)
+    double noise = 0.0;
     double y_mean = 0.0, y_std = 1.0;
     std::vector<double> y_norm;  // host copy of normalised targets (n)
     std::vector<double> y_raw;   // host copy of the raw targets (n)
@@ -366,6 +367,7 @@ static int check_kernel(const b200bo_gp* gp, const b200bo_kernel* k) {
     for (int j = 0; j < k->n_length_scale; ++j)
         if (!(k->length_scale[j] > 0.0)) return set_err(B200BO_ERR_ARG, "length_scale must be > 0");
     if (!(k->const_value > 0.0)) return set_err(B200BO_ERR_ARG, "const_value must be > 0");
+    if (!(k->noise_level >= 0.0)) return set_err(B200BO_ERR_ARG, "noise_level must be >= 0");
     return B200BO_OK;
 }
 
@@ -587,7 +589,7 @@ extern "C" int b200bo_gp_fit(b200bo_gp* gp, const double* X, const double* y, in
     NvtxRange nvtx_range("b200bo:fit");
     if (info) *info = 0;
     int finfo = 0;
-    if ((rc = factorize(gp, kern, alpha, &finfo))) return rc;
+    if ((rc = factorize(gp, kern, alpha + kern->noise_level, &finfo))) return rc;
     if (finfo != 0) {
         if (info) *info = finfo;
         return set_err(B200BO_ERR_NOT_PD, "%d-th leading minor of the array is not positive definite", finfo);
@@ -598,7 +600,8 @@ extern "C" int b200bo_gp_fit(b200bo_gp* gp, const double* X, const double* y, in
     gp->family = kern->family;
     gp->nu = kern->family == B200BO_KERNEL_RBF ? B200BO_NU_INF : kern->nu;
     gp->constv = kern->const_value;
-    gp->jitter = alpha;
+    gp->jitter = alpha + kern->noise_level;
+    gp->noise = kern->noise_level;
     gp->fitted = true;
     return B200BO_OK;
 }
@@ -683,9 +686,12 @@ extern "C" int b200bo_gp_lml(b200bo_gp* gp, const b200bo_kernel* kern, double al
     gp->tc_valid = false;
     const int n = (int)gp->n, np = gp->np, d = gp->d;
     const int aniso = kern->n_length_scale > 1;
-    const int ntheta = (has_const ? 1 : 0) + kern->n_length_scale;
+    const int want_noise = (has_const & 2) ? 1 : 0;
+    has_const &= 1;
+    const int ntheta_k = (has_const ? 1 : 0) + kern->n_length_scale;  // produced by the pair kernel
+    const int ntheta = ntheta_k + want_noise;
     int finfo = 0;
-    if ((rc = factorize(gp, kern, alpha, &finfo))) return rc;
+    if ((rc = factorize(gp, kern, alpha + kern->noise_level, &finfo))) return rc;
     if (finfo != 0) {  // SK/_gpr.py:590-593
         *lml = -std::numeric_limits<double>::infinity();
         if (grad)
@@ -717,16 +723,16 @@ extern "C" int b200bo_gp_lml(b200bo_gp* gp, const b200bo_kernel* kern, double al
             const int nb64 = (n + 63) / 64;
             dim3 grd(nb64, nb64);
             nblk = (size_t)nb64 * (nb64 + 1) / 2;
-            if ((rc = gp->part.reserve(sizeof(double) * nblk * ntheta))) return rc;
+            if ((rc = gp->part.reserve(sizeof(double) * nblk * ntheta_k))) return rc;
             const double* Xsp = gp->Xs.as<double>();
             const double* Ki = gp->T.as<double>();
             const double* al = gp->alphav.as<double>();
             double* pt = gp->part.as<double>();
 #define B200BO_LG(COV)                                                                                              \
     if (aniso)                                                                                                      \
-        lml_grad_tile_kernel<COV, true><<<grd, 256, 0, g_st>>>(Xsp, Ki, np, al, n, d, kern->const_value, has_const, pt, ntheta); \
+        lml_grad_tile_kernel<COV, true><<<grd, 256, 0, g_st>>>(Xsp, Ki, np, al, n, d, kern->const_value, has_const, pt, ntheta_k); \
     else                                                                                                            \
-        lml_grad_tile_kernel<COV, false><<<grd, 256, 0, g_st>>>(Xsp, Ki, np, al, n, d, kern->const_value, has_const, pt, ntheta);
+        lml_grad_tile_kernel<COV, false><<<grd, 256, 0, g_st>>>(Xsp, Ki, np, al, n, d, kern->const_value, has_const, pt, ntheta_k);
             switch (cov) {
                 case 0: B200BO_LG(0) break;
                 case 1: B200BO_LG(1) break;
@@ -737,20 +743,31 @@ extern "C" int b200bo_gp_lml(b200bo_gp* gp, const b200bo_kernel* kern, double al
         } else {
             dim3 grd((n + 15) / 16, (n + 15) / 16);
             nblk = (size_t)grd.x * grd.y;
-            if ((rc = gp->part.reserve(sizeof(double) * nblk * ntheta))) return rc;
+            if ((rc = gp->part.reserve(sizeof(double) * nblk * ntheta_k))) return rc;
             lml_grad_kernel<<<grd, 256, 0, g_st>>>(gp->Xs.as<double>(), gp->T.as<double>(), np, gp->alphav.as<double>(),
                                                    n, d, kern->family,
                                                    kern->family == B200BO_KERNEL_RBF ? B200BO_NU_INF : kern->nu,
-                                                   kern->const_value, has_const, aniso, gp->part.as<double>(), ntheta);
+                                                   kern->const_value, has_const, aniso, gp->part.as<double>(), ntheta_k);
         }
         LAUNCHED();
         CU(cudaGetLastError());
-        std::vector<double> part(nblk * ntheta);
-        if ((rc = d2h(part.data(), gp->part.p, sizeof(double) * nblk * ntheta))) return rc;
-        for (int p = 0; p < ntheta; ++p) {
+        std::vector<double> part(nblk * ntheta_k);
+        if ((rc = d2h(part.data(), gp->part.p, sizeof(double) * nblk * ntheta_k))) return rc;
+        for (int p = 0; p < ntheta_k; ++p) {
             long double s = 0.0L;
-            for (size_t b = 0; b < nblk; ++b) s += part[b * ntheta + p];
+            for (size_t b = 0; b < nblk; ++b) s += part[b * ntheta_k + p];
             grad[p] = (double)s;
+        }
+        if (want_noise) {
+            // dK/dlog(noise_level) = noise_level * I (SK/gaussian_process/kernels.py:1311-1322):
+            // grad = 0.5 * noise_level * sum_i (alpha_i^2 - (K^-1)_ii)
+            diag_kernel<<<(n + 255) / 256, 256, 0, g_st>>>(gp->T.as<double>(), np, gp->v2.as<double>(), n);
+            LAUNCHED();
+            std::vector<double> kd(n);
+            if ((rc = d2h(kd.data(), gp->v2.p, sizeof(double) * n))) return rc;
+            long double sn = 0.0L;
+            for (int i = 0; i < n; ++i) sn += (long double)a[i] * a[i] - (long double)kd[i];
+            grad[ntheta_k] = (double)(0.5L * (long double)kern->noise_level * sn);
         }
     }
     return B200BO_OK;
@@ -931,6 +948,7 @@ static int eval_core(const b200bo_acq* spec, const CandSrc& src, int64_t m, doub
         G.family = gp->family;
         G.nu = gp->nu;
         G.constv = gp->constv;
+        G.prior = gp->constv + gp->noise;
         G.y_mean = gp->y_mean;
         G.y_std = gp->y_std;
         G.lb = spec->lb[g];
@@ -1253,7 +1271,7 @@ extern "C" int b200bo_gp_predict_cov(b200bo_gp* gp, const double* Xc, int64_t m,
     {
         dim3 blk(32, 8), grd((mi + 31) / 32, (mi + 7) / 8);
         cov_finish_kernel<<<grd, blk>>>(gp->cov_xc.as<double>(), gp->cov_c.as<double>(), mp, gp->cov_out.as<double>(),
-                                        mi, d, gp->family, gp->nu, gp->constv, gp->y_std);
+                                        mi, d, gp->family, gp->nu, gp->constv, gp->y_std, gp->noise);
         LAUNCHED();
     }
     CU(cudaGetLastError());
@@ -1385,6 +1403,7 @@ extern "C" int b200bo_gp_replicate(const b200bo_gp* src, int device, b200bo_gp**
     dst->nu = src->nu;
     dst->constv = src->constv;
     dst->jitter = src->jitter;
+    dst->noise = src->noise;
     dst->y_mean = src->y_mean;
     dst->y_std = src->y_std;
     dst->normalize = src->normalize;

@@ -587,13 +587,13 @@ __global__ void cross_mean_kernel(const double* __restrict__ Kst, const double* 
 // cov[i][j] = (k(x_i, x_j) - (V^T V)[i][j]) * y_std^2   (m x m, contiguous)
 __global__ void cov_finish_kernel(const double* __restrict__ Xcs, const double* __restrict__ VtV, int ldv,
                                   double* __restrict__ cov, int m, int d, int family, int nu, double constv,
-                                  double y_std) {
+                                  double y_std, double noise) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= m || j >= m) return;
     double kv;
     if (i == j) {
-        kv = constv;
+        kv = constv + noise;  // kernel_(X) with Y=None: a WhiteKernel term sits on the diagonal
     } else {
         const double* a = Xcs + (size_t)min(i, j) * d;
         const double* b = Xcs + (size_t)max(i, j) * d;

@@ -36,6 +36,7 @@ struct GpDev {
     const uint8_t* linv_tc;  // fp32 mode: L^-1 as tf32 (hi,lo) UMMA operand images, or nullptr
     int n, np, family, nu;
     double constv, y_mean, y_std, lb, ub;
+    double prior;  // prior variance kernel_.diag(x*) = constv + WhiteKernel noise_level
 };
 
 struct PredictParams {
@@ -90,7 +91,7 @@ __device__ __forceinline__ void candidate_epilogue(const PredictParams& P, const
                                                    double mu_n, double colsq, long long gi,
                                                    double& base_neg, double& prod, double* final_val = nullptr) {
     const double mean = G.y_std * mu_n + G.y_mean;
-    double var = G.constv - colsq;
+    double var = G.prior - colsq;
     if (var < 0.0) {
         var = 0.0;
         if (P.clamp_count && gi < P.m) atomicAdd(P.clamp_count, 1ull);

@@ -21,7 +21,7 @@ import numpy as np
 import scipy.optimize
 from sklearn.base import clone
 from sklearn.gaussian_process import GaussianProcessRegressor
-from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern, Product
+from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern, Product, Sum, WhiteKernel
 from sklearn.utils import check_random_state
 from sklearn.utils.optimize import _check_optimize_result
 
@@ -52,7 +52,8 @@ def find_transform(kernel):
 class EngineKernel:
     """What the device needs to know about a sklearn kernel, plus the theta <-> parameter map."""
 
-    def __init__(self, family, nu, const_value, length_scale, const_free, ls_free, const_first):
+    def __init__(self, family, nu, const_value, length_scale, const_free, ls_free, const_first,
+                 noise=0.0, noise_free=False, noise_first=False):
         self.family = family
         self.nu = nu
         self.const_value = float(const_value)
@@ -60,19 +61,25 @@ class EngineKernel:
         self.const_free = const_free    # ConstantKernel present and not "fixed"
         self.ls_free = ls_free
         self.const_first = const_first  # theta order: [const, ls] (k1=Constant) or [ls, const]
+        self.noise = float(noise)       # WhiteKernel term of a Sum (0 = absent)
+        self.noise_free = noise_free
+        self.noise_first = noise_first  # Sum(WhiteKernel, k): the noise theta comes first
 
     def c_spec(self):
         self._ls_keep = np.ascontiguousarray(self.length_scale, dtype=np.float64)
         return B.KernelSpec(self.family, self.nu, int(self._ls_keep.size), 0, self.const_value,
-                            B.as_dp(self._ls_keep))
+                            B.as_dp(self._ls_keep), self.noise)
 
     def with_theta(self, theta):
         """Engine kernel with the free hyper-parameters replaced by exp(theta)."""
         theta = np.asarray(theta, dtype=np.float64)
         k = EngineKernel(self.family, self.nu, self.const_value, self.length_scale, self.const_free,
-                         self.ls_free, self.const_first)
+                         self.ls_free, self.const_first, self.noise, self.noise_free, self.noise_first)
         nls = self.length_scale.size if self.ls_free else 0
         pos = 0
+        if self.noise_free and self.noise_first:
+            k.noise = float(np.exp(theta[pos]))
+            pos += 1
         if self.const_free and self.const_first:
             k.const_value = float(np.exp(theta[pos]))
             pos += 1
@@ -82,22 +89,22 @@ class EngineKernel:
         if self.const_free and not self.const_first:
             k.const_value = float(np.exp(theta[pos]))
             pos += 1
+        if self.noise_free and not self.noise_first:
+            k.noise = float(np.exp(theta[pos]))
+            pos += 1
         if pos != theta.size:
             raise ValueError("theta has the wrong number of entries")
         return k
 
     def select_grad(self, g_dev):
-        """Device gradient order is [const (if has_const)], ls...; reorder/select to theta order."""
+        """Device gradient order is [const (if free)], ls..., [noise (if free)]; reorder/select to theta order."""
         nls = self.length_scale.size
         off = 1 if self.const_free else 0
-        parts = []
         g_c = g_dev[:off]
         g_l = g_dev[off:off + nls] if self.ls_free else g_dev[:0]
-        if self.const_first:
-            parts = [g_c, g_l]
-        else:
-            parts = [g_l, g_c]
-        return np.concatenate(parts)
+        g_n = g_dev[off + nls:off + nls + 1] if self.noise_free else g_dev[:0]
+        inner = [g_c, g_l] if self.const_first else [g_l, g_c]
+        return np.concatenate([g_n] + inner if self.noise_first else inner + [g_n])
 
 
 _NU_CODES = {0.5: B.NU_05, 1.5: B.NU_15, 2.5: B.NU_25, np.inf: B.NU_INF}
@@ -118,7 +125,20 @@ def _parse_base(k):
 
 def parse_kernel(kernel) -> EngineKernel:
     """sklearn kernel -> EngineKernel.  Supported set: {Matern nu in (.5,1.5,2.5,inf), RBF},
-    iso/anisotropic, x ConstantKernel (either order).  Anything else: NotImplementedError."""
+    iso/anisotropic, x ConstantKernel (either order), + WhiteKernel (either order).  Anything else:
+    NotImplementedError."""
+    if isinstance(kernel, Sum):
+        k1, k2 = kernel.k1, kernel.k2
+        if isinstance(k1, WhiteKernel) == isinstance(k2, WhiteKernel):
+            raise NotImplementedError("only {Matern, RBF}[* ConstantKernel] + WhiteKernel sums are supported")
+        white, other, first = (k1, k2, True) if isinstance(k1, WhiteKernel) else (k2, k1, False)
+        if isinstance(other, Sum):
+            raise NotImplementedError("nested kernel sums are not supported by the B200 engine")
+        ek = parse_kernel(other)
+        ek.noise = float(white.noise_level)
+        ek.noise_free = not white.hyperparameter_noise_level.fixed
+        ek.noise_first = first
+        return ek
     if isinstance(kernel, Product):
         k1, k2 = kernel.k1, kernel.k2
         if isinstance(k1, ConstantKernel) and not isinstance(k2, ConstantKernel):
@@ -134,13 +154,19 @@ def parse_kernel(kernel) -> EngineKernel:
     return EngineKernel(fam, nu, 1.0, ls, False, not ls_fixed, True)
 
 
+def _find_transform_deep(kernel):
+    """find_transform on the kernel itself or, for Product / Sum, on its operands."""
+    t = find_transform(kernel)
+    if t is None and isinstance(kernel, (Product, Sum)):
+        t = _find_transform_deep(kernel.k1) or _find_transform_deep(kernel.k2)
+    return t
+
+
 def probe_transform(kernel, d):
     """bayes_opt's wrap_kernel (R/bayes_opt/parameter.py:457-495) stores the input transform on
     the kernel as ``_transform``.  The engine supports per-dimension identity / np.round; the
     transform is identified by probing it (it is an opaque callable)."""
-    t = find_transform(kernel)
-    if t is None and isinstance(kernel, Product):
-        t = find_transform(kernel.k1) or find_transform(kernel.k2)
+    t = _find_transform_deep(kernel)
     if t is None:
         return None
     probe = np.array([[0.3 + j for j in range(d)], [1.7 - j for j in range(d)], [2.5 + j for j in range(d)]])
@@ -168,9 +194,7 @@ def resolve_transform(kernel, d):
                               callable is applied to the batch on the host exactly where the reference
                               applies it (WrappedKernel.__call__, parameter.py:484-487) and the device
                               sees the transformed coordinates."""
-    t = find_transform(kernel)
-    if t is None and isinstance(kernel, Product):
-        t = find_transform(kernel.k1) or find_transform(kernel.k2)
+    t = _find_transform_deep(kernel)
     if t is None:
         return "device", None
     try:
@@ -556,7 +580,7 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
         return True
 
     def _fit_signature(self, ek):
-        return (ek.family, ek.nu, ek.const_value, tuple(ek.length_scale.tolist()), float(self.alpha),
+        return (ek.family, ek.nu, ek.const_value, tuple(ek.length_scale.tolist()), ek.noise, float(self.alpha),
                 bool(self.normalize_y), self.precision)
 
     def _constrained_optimization(self, obj_func, initial_theta, bounds):
@@ -574,9 +598,10 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
         h = handle if handle is not None else self._handle()
         spec = ek.c_spec()
         lml = C.c_double(0.0)
-        ntheta_dev = (1 if ek.const_free else 0) + ek.length_scale.size
+        ntheta_dev = (1 if ek.const_free else 0) + ek.length_scale.size + (1 if ek.noise_free else 0)
         grad = np.zeros(ntheta_dev)
-        B.check(B.lib().b200bo_gp_lml(h.ptr, C.byref(spec), float(self.alpha), int(ek.const_free),
+        B.check(B.lib().b200bo_gp_lml(h.ptr, C.byref(spec), float(self.alpha),
+                                      int(ek.const_free) | (2 if ek.noise_free else 0),
                                       C.byref(lml), B.as_dp(grad) if eval_gradient else None))
         self.__dict__["_b200_device_fitted"] = False  # factor buffers now hold this theta
         if eval_gradient:

@@ -64,8 +64,10 @@ extern "C" {
 
 typedef struct b200bo_gp b200bo_gp; /* opaque: one GP's device-resident factorisation */
 
-/* kernel hyper-parameters: const_value * k(x/length_scale, x'/length_scale)
- * (ConstantKernel * {Matern,RBF}; const_value = 1 for a bare kernel). */
+/* kernel hyper-parameters: const_value * k(x/length_scale, x'/length_scale) [+ noise_level * delta(x, x')]
+ * (ConstantKernel * {Matern,RBF} [+ WhiteKernel]; const_value = 1 for a bare kernel, noise_level = 0 without a
+ * WhiteKernel term, SK/gaussian_process/kernels.py:1205-1330: the term adds noise_level to the diagonal of K(X,X)
+ * and to the prior variance kernel_.diag(X*), and nothing to K(X*,X)). */
 typedef struct {
     int32_t family;            /* B200BO_KERNEL_* */
     int32_t nu;                /* B200BO_NU_* (ignored for RBF) */
@@ -73,6 +75,7 @@ typedef struct {
     int32_t reserved;
     double const_value;        /* ConstantKernel factor; 1.0 when absent */
     const double* length_scale;/* host pointer, n_length_scale entries */
+    double noise_level;        /* WhiteKernel term; 0.0 when absent */
 } b200bo_kernel;
 
 /* One acquisition evaluation: the closure built by AcquisitionFunction._get_acq
@@ -147,8 +150,8 @@ int b200bo_gp_append(b200bo_gp* gp, const double* x_new, double y_new, int64_t* 
 /* Replaces GaussianProcessRegressor.log_marginal_likelihood(theta, eval_gradient)
  * (SK/gaussian_process/_gpr.py:541-656) on the training set of the last b200bo_gp_set_data /
  * b200bo_gp_fit call.  grad (nullable) receives d LML / d log(theta): [log const_value if
- * has_const], then log length_scale (1 or d entries).  Non-PD -> *lml = -inf, grad = 0 (as
- * :590-593) and the call still returns B200BO_OK. */
+ * has_const & 1], then log length_scale (1 or d entries), then [log noise_level if has_const & 2].
+ * Non-PD -> *lml = -inf, grad = 0 (as :590-593) and the call still returns B200BO_OK. */
 int b200bo_gp_set_data(b200bo_gp* gp, const double* X, const double* y, int64_t n, int d,
                        int normalize_y);
 int b200bo_gp_lml(b200bo_gp* gp, const b200bo_kernel* kern, double alpha, int has_const,

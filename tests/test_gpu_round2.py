@@ -319,3 +319,40 @@ def test_tiled_lml_gradient_kernel_families(bo, tag):
     l0, g0 = sk.log_marginal_likelihood(theta, eval_gradient=True)
     assert l1 == pytest.approx(l0, rel=1e-8)
     assert_allclose(g1, g0, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("order", ["kernel_first", "white_first"])
+def test_white_kernel_term_vs_sklearn(bo, order):
+    """Sum(k, WhiteKernel): noise on the diagonal of K(X,X) and in the prior variance, nothing in K(X*,X)
+    (SK/gaussian_process/kernels.py:1205-1330); LML, its gradient incl. d/dlog(noise), a full fit with restarts,
+    predict(return_std / return_cov) against sklearn."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import ConstantKernel, WhiteKernel
+
+    X, y = _synth(150, 3, 6)
+    base = ConstantKernel(1.5) * Matern(nu=2.5, length_scale=0.8)
+    k = base + WhiteKernel(0.05) if order == "kernel_first" else WhiteKernel(0.05) + base
+    xt = np.random.RandomState(1).uniform(size=(40, 3))
+    gp = bo.B200GaussianProcessRegressor(kernel=k, alpha=1e-8, normalize_y=True, optimizer=None).fit(X, y)
+    sk = GaussianProcessRegressor(kernel=k, alpha=1e-8, normalize_y=True, optimizer=None).fit(X, y)
+    mu, sd = gp.predict(xt, return_std=True)
+    mu0, sd0 = sk.predict(xt, return_std=True)
+    assert_allclose(mu, mu0, rtol=1e-7, atol=1e-9)
+    assert_allclose(sd, sd0, rtol=1e-7, atol=1e-9)
+    assert_allclose(gp.predict(xt[:9], return_cov=True)[1], sk.predict(xt[:9], return_cov=True)[1], rtol=1e-6, atol=1e-9)
+    theta = k.theta + np.array([0.3, -0.2, 0.4][: k.theta.size])
+    l1, g1 = gp.log_marginal_likelihood(theta, eval_gradient=True)
+    l0, g0 = sk.log_marginal_likelihood(theta, eval_gradient=True)
+    assert l1 == pytest.approx(l0, rel=1e-9)
+    assert_allclose(g1, g0, rtol=1e-6, atol=1e-7)
+    # full fit: same RandomState consumption and optimum to optimiser tolerance
+    r1, r0 = np.random.RandomState(4), np.random.RandomState(4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gpf = bo.B200GaussianProcessRegressor(kernel=k, alpha=1e-8, normalize_y=True, n_restarts_optimizer=2,
+                                              random_state=r1).fit(X, y)
+        skf = GaussianProcessRegressor(kernel=k, alpha=1e-8, normalize_y=True, n_restarts_optimizer=2,
+                                       random_state=r0).fit(X, y)
+    assert r1.uniform() == r0.uniform()
+    assert gpf.log_marginal_likelihood_value_ == pytest.approx(skf.log_marginal_likelihood_value_, rel=1e-6, abs=1e-6)
+    assert_allclose(gpf.kernel_.theta, skf.kernel_.theta, rtol=0, atol=5e-3)

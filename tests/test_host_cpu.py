@@ -7,7 +7,7 @@ import sys
 
 import numpy as np
 import pytest
-from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern, RationalQuadratic
+from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern, RationalQuadratic, WhiteKernel
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -38,7 +38,7 @@ def test_library_exports_every_header_symbol(bo):
 def test_struct_layouts_match_header(bo):
     from bayesianoptimization_b200 import _lib as B
 
-    assert C.sizeof(B.KernelSpec) == 32
+    assert C.sizeof(B.KernelSpec) == 40
     assert C.sizeof(B.AcqSpec) == 16 + 24 + 8 * B.MAX_GPS * 3
 
 
@@ -88,9 +88,24 @@ def test_kernel_parsing(bo):
     assert list(k.select_grad(np.array([10.0, 20.0]))) == [20.0, 10.0]
     k = parse_kernel(ConstantKernel(1.0, constant_value_bounds="fixed") * RBF(1.0, length_scale_bounds="fixed"))
     assert not k.const_free and not k.ls_free
-    for bad in (RationalQuadratic(), Matern(nu=0.7), RBF() + RBF()):
+    for bad in (RationalQuadratic(), Matern(nu=0.7), RBF() + RBF(), WhiteKernel() + WhiteKernel(),
+                (RBF() + WhiteKernel()) + WhiteKernel()):
         with pytest.raises(NotImplementedError):
             parse_kernel(bad)
+    # + WhiteKernel (either order): theta layout of sklearn's Sum is k1.theta ++ k2.theta
+    ks = ConstantKernel(2.0) * Matern(nu=2.5, length_scale=[0.5, 0.7]) + WhiteKernel(0.01)
+    k = parse_kernel(ks)
+    assert (k.noise, k.noise_free, k.noise_first, k.const_free) == (0.01, True, False, True)
+    k2 = k.with_theta(ks.theta)
+    assert k2.const_value == pytest.approx(2.0) and list(k2.length_scale) == pytest.approx([0.5, 0.7])
+    assert k2.noise == pytest.approx(0.01)
+    assert list(k.select_grad(np.array([1.0, 2.0, 3.0, 4.0]))) == [1.0, 2.0, 3.0, 4.0]
+    kw = WhiteKernel(0.3) + RBF(1.5)
+    k = parse_kernel(kw)
+    assert k.noise_first and k.with_theta(kw.theta).noise == pytest.approx(0.3)
+    assert list(k.select_grad(np.array([7.0, 9.0]))) == [9.0, 7.0]  # device order [ls, noise] -> theta [noise, ls]
+    k = parse_kernel(WhiteKernel(0.3, noise_level_bounds="fixed") + RBF(1.5))
+    assert not k.noise_free and list(k.select_grad(np.array([7.0]))) == [7.0]
 
 
 def test_transform_probe(bo, ref):

@@ -37,5 +37,20 @@ if [ "$mode" = "prof" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:predict_acq_kernel -s 3 -c 1 -o $out/prof_predict -f \
      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > $out/ncu_full.log 2>&1
   echo "ncu full exit $?"
+  echo "== ncu full (fp32-mode kernel)"
+  B200BO_PREDICT_IMPL=tf32 timeout 900 ncu --set full --clock-control none --import-source on -k regex:predict_acq_tc2 -s 3 -c 1 -o $out/prof_predict_tc2 -f \
+     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > $out/ncu_full_tc2.log 2>&1
+  echo "ncu tc2 exit $?"
+  echo "== ncu launch list + full captures of the fit-side kernels (one LML+gradient evaluation, N=4096)"
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches_lml.csv python tools/lml_once.py > $out/lml_once.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:dgemm128 -s 130 -c 6 -o $out/prof_fit_gemm -f python tools/lml_once.py > $out/ncu_fit_gemm.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"potrf_diag|lml_grad|kbuild" -s 66 -c 4 -o $out/prof_fit_misc -f python tools/lml_once.py > $out/ncu_fit_misc.log 2>&1
+  echo "ncu fit exit $?"
+fi
+if [ "$mode" = "variants" ]; then
+  for w in 8 16; do
+    B200BO_PREDICT_WARPS=$w timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extra > $out/bench_warps$w.json 2> $out/bench_warps$w.err
+    echo "warps=$w exit $?"; cat $out/bench_warps$w.json
+  done
 fi
 ls -la $out | tail -n 24
