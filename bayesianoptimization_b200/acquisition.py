@@ -66,10 +66,19 @@ class DeviceHooks(abc.ABC):
             return acq
         return FusedAcquisition(kind, gp, constraint, owner=self)
 
+    # "host_rng": the candidates are TargetSpace.random_sample's MT19937 stream (parity with the reference);
+    # "device_philox": throughput mode - they are generated inside the fused kernel (continuous spaces only;
+    # ONE 64-bit seed is drawn from the caller's RandomState per call).  Set by enable(candidate_source=...).
+    b200_candidate_source = "host_rng"
+
     def _random_sample_minimize(self, acq, space, random_state, n_random, n_x_seeds=0):
         if n_random == 0 or not isinstance(acq, FusedAcquisition) or n_x_seeds > B.MAX_TOPK:
             # (n_smart beyond the device's top-k capacity: evaluate on the device, select with numpy)
             return super()._random_sample_minimize(acq, space, random_state, n_random, n_x_seeds)
+        if self.b200_candidate_source == "device_philox" and all(space.continuous_dimensions):
+            seed = int(random_state.randint(0, 2**32, dtype=np.uint64)) << 32 | int(random_state.randint(0, 2**32, dtype=np.uint64))
+            _, min_acq, x_min, _, x_seeds = acq.argmin_topk_philox(seed, space.bounds, n_random, n_x_seeds)
+            return x_min, min_acq, (x_seeds if n_x_seeds != 0 else [])
         x_tries = space.random_sample(n_random, random_state=random_state)  # the reference's RNG stream
         idx, min_acq, top = acq.argmin_topk(x_tries, n_x_seeds)
         return x_tries[idx], min_acq, (x_tries[top] if n_x_seeds != 0 else [])
@@ -118,17 +127,21 @@ _HOOKED = {
 }
 
 
-def accelerate(acq):
+def accelerate(acq, candidate_source=None):
     """Give an existing reference acquisition object the device hooks IN PLACE (all state kept: kappa/xi,
     decay counters, dummies, gains).  ConstantLiar / GPHedge only orchestrate: their base acquisitions are
     accelerated, the wrappers stay what they are."""
-    if isinstance(acq, DeviceHooks):
-        return acq
+    if candidate_source not in (None, "host_rng", "device_philox"):
+        raise ValueError("candidate_source must be 'host_rng' or 'device_philox'")
     if isinstance(acq, _ref.ConstantLiar):
-        acq.base_acquisition = accelerate(acq.base_acquisition)
+        acq.base_acquisition = accelerate(acq.base_acquisition, candidate_source)
         return acq
     if isinstance(acq, _ref.GPHedge):
-        acq.base_acquisitions = [accelerate(a) for a in acq.base_acquisitions]
+        acq.base_acquisitions = [accelerate(a, candidate_source) for a in acq.base_acquisitions]
+        return acq
+    if candidate_source is not None:
+        acq.b200_candidate_source = candidate_source
+    if isinstance(acq, DeviceHooks):
         return acq
     cls = type(acq)
     hooked = _HOOKED.get(cls)

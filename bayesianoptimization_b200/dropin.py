@@ -15,17 +15,21 @@ from __future__ import annotations
 from .gpr import to_b200_gp
 
 
-def accelerate_acquisition(acq):
+def accelerate_acquisition(acq, candidate_source=None):
     from .acquisition import accelerate
 
-    return accelerate(acq)
+    return accelerate(acq, candidate_source)
 
 
-def enable(optimizer, device=0, devices=None, precision="fp64"):
-    """Make ``optimizer.suggest()`` / ``maximize()`` / ``predict()`` run on the B200."""
+def enable(optimizer, device=0, devices=None, precision="fp64", candidate_source="host_rng"):
+    """Make ``optimizer.suggest()`` / ``maximize()`` / ``predict()`` run on the B200.
+
+    candidate_source  "host_rng" (default): the random candidates of every suggest() are the reference's own
+                      MT19937 stream (parity mode); "device_philox": generated inside the fused kernel
+                      (throughput mode, continuous spaces; results are valid but differ from the reference's run)."""
     optimizer._gp = to_b200_gp(optimizer._gp, device, devices, precision)
     cm = getattr(optimizer._space, "_constraint", None)
     if cm is not None:
         cm._model = [to_b200_gp(g, device, devices, precision) for g in cm._model]
-    optimizer._acquisition_function = accelerate_acquisition(optimizer._acquisition_function)
+    optimizer._acquisition_function = accelerate_acquisition(optimizer._acquisition_function, candidate_source)
     return optimizer

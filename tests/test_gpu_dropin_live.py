@@ -219,3 +219,27 @@ def test_maximize_runs_end_to_end_on_device(ref, bo):
         opt.maximize(init_points=3, n_iter=6)
     assert len(opt.space) == 9 and B.lib().b200bo_launch_count() > n0
     assert opt.max["target"] > -3.5  # the maximum on this domain is f(2, 1) = -3
+
+
+def test_throughput_mode_candidate_source_through_the_driver(ref, bo):
+    """enable(optimizer, candidate_source="device_philox"): the random candidates of suggest() are generated
+    inside the fused kernel (no MT19937 stream, no H2D).  Opt-in: results are valid, not the reference's run."""
+    from numpy.testing import assert_allclose
+
+    opt = ref.BayesianOptimization(f=readme_f, pbounds={"x": (2, 4), "y": (-3, 3)}, random_state=1, verbose=0)
+    bo.enable(opt, candidate_source="device_philox")
+    a = opt._acquisition_function
+    assert a.b200_candidate_source == "device_philox"
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        opt.maximize(init_points=4, n_iter=4)
+        a._fit_gp(opt._gp, opt._space)
+        f = a._get_acq(gp=opt._gp)
+        x_min, v, seeds = a._random_sample_minimize(f, opt._space, np.random.RandomState(2), n_random=50_000, n_x_seeds=6)
+    b = opt._space.bounds
+    assert x_min.shape == (2,) and np.all(x_min >= b[:, 0]) and np.all(x_min <= b[:, 1])
+    assert seeds.shape == (6, 2) and np.all(seeds >= b[:, 0]) and np.all(seeds <= b[:, 1])
+    assert_allclose(f(x_min)[0], v, rtol=1e-9, atol=1e-12)          # the regenerated row is the evaluated row
+    vals = f(seeds)
+    assert np.all(np.diff(vals) >= -1e-12) and abs(vals[0] - v) <= 1e-9 * max(1.0, abs(v))
+    assert opt.max["target"] > -3.5
