@@ -46,6 +46,9 @@ if [ "$mode" = "prof" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:dgemm128 -s 130 -c 6 -o $out/prof_fit_gemm -f python tools/lml_once.py > $out/ncu_fit_gemm.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"potrf_diag|lml_grad|kbuild" -s 66 -c 4 -o $out/prof_fit_misc -f python tools/lml_once.py > $out/ncu_fit_misc.log 2>&1
   echo "ncu fit exit $?"
+  echo "== ncu launch list of one suggest() without refit (small-batch kernels)"
+  REPS=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches_suggest.csv python tools/suggest_once.py > $out/suggest_once.log 2>&1
+  tail -2 $out/suggest_once.log
 fi
 if [ "$mode" = "variants" ]; then
   for w in 8 16; do
