@@ -116,6 +116,11 @@ struct b200bo_gp {
     cudaStream_t bulk_stream = nullptr;
     cudaEvent_t ev_chain = nullptr, ev_bulk = nullptr;
     DevBuf pside;
+    // CUDA graph of the theta-independent part of a factorisation (run_factor)
+    cudaStream_t cap_stream = nullptr;
+    cudaGraphExec_t fgraph_exec = nullptr;
+    unsigned long long fgraph_key[16] = {0};
+    long long fgraph_nodes = 0;
     // streamed host batches: copy / execute streams and the double-buffer events
     cudaStream_t copy_stream = nullptr, exec_stream = nullptr;
     cudaEvent_t chunk_up[2] = {nullptr, nullptr}, chunk_done[2] = {nullptr, nullptr};
@@ -236,6 +241,8 @@ extern "C" void b200bo_gp_destroy(b200bo_gp* gp) {
                       &gp->sel_cta, &gp->pbounds, &gp->prow, &gp->pside};
     for (DevBuf* b : bufs) b->release();
     if (gp->stream) cudaStreamDestroy(gp->stream);
+    if (gp->fgraph_exec) cudaGraphExecDestroy(gp->fgraph_exec);
+    if (gp->cap_stream) cudaStreamDestroy(gp->cap_stream);
     if (gp->bulk_stream) cudaStreamDestroy(gp->bulk_stream);
     if (gp->ev_chain) cudaEventDestroy(gp->ev_chain);
     if (gp->ev_bulk) cudaEventDestroy(gp->ev_bulk);
@@ -371,6 +378,17 @@ static int check_kernel(const b200bo_gp* gp, const b200bo_kernel* k) {
     return B200BO_OK;
 }
 
+static int potrf_mode() {  // 0 look-ahead (default), 1 serial blocked, 2 legacy unblocked
+    const char* pv = getenv("B200BO_POTRF");
+    if (pv && (pv[0] == 'l' || pv[0] == 'L')) return 2;
+    if (pv && (pv[0] == 's' || pv[0] == 'S')) return 1;
+    return 0;
+}
+static bool gemm_force64() {
+    const char* e = getenv("B200BO_GEMM");
+    return e && e[0] == '6';
+}
+
 static int ensure_bulk_stream(b200bo_gp* gp) {
     if (!gp->bulk_stream) {
         CU(cudaStreamCreateWithFlags(&gp->bulk_stream, cudaStreamNonBlocking));
@@ -387,8 +405,7 @@ static int gemm(int M, int N, int K, double alpha, const double* A, int lda, lon
     if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return B200BO_OK;
     const cudaStream_t st = stp ? *stp : g_st;
     // 128x128 pipelined tiles wherever a tile can be filled; the 64x64 kernel for narrow panels / small blocks
-    static const bool force64 = [] { const char* e = getenv("B200BO_GEMM"); return e && e[0] == '6'; }();
-    if (M >= 128 && N >= 128 && !force64) {
+    if (M >= 128 && N >= 128 && !gemm_force64()) {
         dim3 grid((N + 127) / 128, (M + 127) / 128, batch);
         dgemm128_kernel<TA, TB><<<grid, 256, kGemm128SmemBytes, st>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta,
                                                                       C, ldc, sC, lower_only, kmode, skip);
@@ -404,32 +421,17 @@ static int gemm(int M, int N, int K, double alpha, const double* A, int lda, lon
 
 // K build + Cholesky + explicit triangular inverse.  On return L holds the clean lower factor,
 // W = L^-1 (lower).  *info_out = 0 or the failing pivot (1-based).
-static int factorize(b200bo_gp* gp, const b200bo_kernel* kern, double jitter, int* info_out) {
-    const int n = (int)gp->n, np = gp->np, d = gp->d;
-    double ls[B200BO_MAX_DIM];
-    for (int j = 0; j < d; ++j) ls[j] = kern->length_scale[kern->n_length_scale == 1 ? 0 : j];
+static int transpose_W(b200bo_gp* gp);
+static int solve_alpha(b200bo_gp* gp);
+
+// Everything of a factorisation whose kernel ARGUMENTS do not depend on the hyper-parameters: K -> L, blocked
+// Cholesky, zeroing of the upper triangle, L^-1 by recursive doubling, its transpose, alpha_ = K^-1 y.  Issued on g_st
+// (+ the bulk stream of the look-ahead); no host synchronisation, no allocation: the sequence is CUDA-graph capturable.
+// A non-positive pivot is replaced by 1 inside the diagonal kernel (arithmetic stays finite) and reported through
+// gp->info, which the caller reads afterwards.
+static int factor_body(b200bo_gp* gp) {
+    const int np = gp->np;
     int rc;
-    if ((rc = h2d(gp->ls.p, ls, sizeof(double) * d))) return rc;
-    const int* xf = gp->xform.empty() ? nullptr : gp->xf.as<int>();
-    {
-        const long long tot = (long long)np * d;
-        scale_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, g_st>>>(gp->X.as<double>(), gp->ls.as<double>(), xf,
-                                                               gp->Xs.as<double>(), n, np, d);
-        LAUNCHED();
-    }
-    {
-        dim3 blk(32, 8), grd(np / 32, np / 32);
-        double* Kp = gp->K.as<double>();
-        const double* Xsp = gp->Xs.as<double>();
-        switch (cov_code(kern->family, kern->nu)) {
-            case 0: kbuild_kernel<0><<<grd, blk, 0, g_st>>>(Xsp, Kp, n, np, d, kern->const_value, jitter); break;
-            case 1: kbuild_kernel<1><<<grd, blk, 0, g_st>>>(Xsp, Kp, n, np, d, kern->const_value, jitter); break;
-            case 2: kbuild_kernel<2><<<grd, blk, 0, g_st>>>(Xsp, Kp, n, np, d, kern->const_value, jitter); break;
-            default: kbuild_kernel<3><<<grd, blk, 0, g_st>>>(Xsp, Kp, n, np, d, kern->const_value, jitter); break;
-        }
-        LAUNCHED();
-    }
-    CU(cudaGetLastError());
     double* L = gp->L.as<double>();
     double* W = gp->W.as<double>();
     double* T = gp->T.as<double>();
@@ -439,9 +441,7 @@ static int factorize(b200bo_gp* gp, const b200bo_kernel* kern, double jitter, in
     // right-looking blocked Cholesky, panel width 64.  B200BO_POTRF=legacy selects the first
     // (unblocked) diagonal-block kernel, B200BO_POTRF=serial the blocked kernel without look-ahead, for A/B
     // measurements.
-    const char* pv = getenv("B200BO_POTRF");
-    const bool legacy_potrf = pv && (pv[0] == 'l' || pv[0] == 'L');
-    const bool serial_potrf = pv && (pv[0] == 's' || pv[0] == 'S');
+    const bool legacy_potrf = potrf_mode() == 2, serial_potrf = potrf_mode() == 1;
     if (legacy_potrf || serial_potrf || np <= 128) {
         for (int j0 = 0; j0 < np; j0 += 64) {
             if (legacy_potrf)
@@ -471,10 +471,7 @@ static int factorize(b200bo_gp* gp, const b200bo_kernel* kern, double jitter, in
         // panel j itself (potrf_diag_kernel, look-ahead form) from a copy of A[j+1, j] taken before the bulk
         // panel solve, and the bulk trailing update leaves block (j+1, j+1) alone.  Every value is produced by
         // exactly one kernel: the result does not depend on how the two streams interleave.
-        int rc2;
-        if ((rc2 = ensure_bulk_stream(gp))) return rc2;
         const cudaStream_t sb = gp->bulk_stream;
-        if ((rc = gp->pside.reserve(sizeof(double) * 64 * 64))) return rc;
         double* Pside = gp->pside.as<double>();
         CU(cudaEventRecord(gp->ev_chain, g_st));
         CU(cudaStreamWaitEvent(sb, gp->ev_chain, 0));  // K build / copies issued so far
@@ -510,10 +507,6 @@ static int factorize(b200bo_gp* gp, const b200bo_kernel* kern, double jitter, in
         zero_upper_kernel<<<grd, blk, 0, g_st>>>(L, np);
         LAUNCHED();
     }
-    int info = 0;
-    if ((rc = d2h(&info, gp->info.p, sizeof(int)))) return rc;
-    *info_out = info;
-    if (info != 0) return B200BO_OK;
     // W = L^-1 by recursive doubling over diagonal blocks:
     //   inv([[A,0],[C,B]]) = [[A^-1,0],[-B^-1 C A^-1, B^-1]]
     for (int s = 64; s < np; s *= 2) {
@@ -545,6 +538,98 @@ static int factorize(b200bo_gp* gp, const b200bo_kernel* kern, double jitter, in
         }
     }
     CU(cudaGetLastError());
+    if ((rc = transpose_W(gp))) return rc;
+    return solve_alpha(gp);
+}
+
+
+// One LML evaluation is ~350 dependent launches and ~250 event operations: issued one by one the HOST is the
+// bottleneck (2-3 us per call, the kernels of a 64-wide step are shorter than that).  The sequence has the same
+// arguments whatever theta is, so it is captured ONCE per handle and training-set size into a CUDA graph (both
+// streams of the look-ahead join the capture) and replayed with one call.  B200BO_GRAPH=0 issues it directly.
+static int run_factor(b200bo_gp* gp) {
+    int rc;
+    if ((rc = ensure_bulk_stream(gp))) return rc;
+    if ((rc = gp->pside.reserve(sizeof(double) * 64 * 64))) return rc;
+    const char* ge = getenv("B200BO_GRAPH");
+    if (ge && ge[0] == '0') return factor_body(gp);
+    const unsigned long long key[] = {(unsigned long long)gp->np, (unsigned long long)gp->K.p, (unsigned long long)gp->L.p,
+                                      (unsigned long long)gp->W.p, (unsigned long long)gp->WT.p, (unsigned long long)gp->T.p,
+                                      (unsigned long long)gp->alphav.p, (unsigned long long)gp->y.p, (unsigned long long)gp->v1.p,
+                                      (unsigned long long)gp->v2.p, (unsigned long long)gp->info.p, (unsigned long long)gp->pside.p,
+                                      (unsigned long long)(potrf_mode() * 2 + (gemm_force64() ? 1 : 0))};
+    constexpr int NKEY = sizeof(key) / sizeof(key[0]);
+    if (!gp->fgraph_exec || memcmp(key, gp->fgraph_key, sizeof(key)) != 0) {
+        if (gp->fgraph_exec) {
+            cudaGraphExecDestroy(gp->fgraph_exec);
+            gp->fgraph_exec = nullptr;
+        }
+        if (!gp->cap_stream) CU(cudaStreamCreateWithFlags(&gp->cap_stream, cudaStreamNonBlocking));
+        const long long before = g_launches.load();
+        cudaStream_t saved = g_st;
+        g_st = gp->cap_stream;
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(gp->cap_stream, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            rc = factor_body(gp);
+            e = cudaStreamEndCapture(gp->cap_stream, &graph);
+            if (rc == B200BO_OK && e == cudaSuccess) e = cudaGraphInstantiate(&gp->fgraph_exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+        }
+        g_st = saved;
+        gp->fgraph_nodes = g_launches.load() - before;
+        g_launches.store(before);  // nothing ran during the capture
+        if (rc != B200BO_OK || e != cudaSuccess || !gp->fgraph_exec) {
+            cudaGetLastError();
+            gp->fgraph_exec = nullptr;
+            static bool warned = false;
+            if (!warned) {
+                warned = true;
+                fprintf(stderr, "b200bo: CUDA-graph capture of the factorisation failed (%s); issuing the launches directly\n",
+                        e != cudaSuccess ? cudaGetErrorString(e) : g_err);
+            }
+            return factor_body(gp);
+        }
+        static_assert(NKEY <= 16, "key");
+        memcpy(gp->fgraph_key, key, sizeof(key));
+    }
+    CU(cudaGraphLaunch(gp->fgraph_exec, g_st));
+    g_launches.fetch_add(gp->fgraph_nodes, std::memory_order_relaxed);
+    return B200BO_OK;
+}
+
+// K build + Cholesky + explicit triangular inverse + alpha_.  On return L holds the clean lower factor,
+// W = L^-1 (lower), WT its transpose.  *info_out = 0 or the failing pivot (1-based).
+static int factorize(b200bo_gp* gp, const b200bo_kernel* kern, double jitter, int* info_out) {
+    const int n = (int)gp->n, np = gp->np, d = gp->d;
+    double ls[B200BO_MAX_DIM];
+    for (int j = 0; j < d; ++j) ls[j] = kern->length_scale[kern->n_length_scale == 1 ? 0 : j];
+    int rc;
+    if ((rc = h2d(gp->ls.p, ls, sizeof(double) * d))) return rc;
+    const int* xf = gp->xform.empty() ? nullptr : gp->xf.as<int>();
+    {
+        const long long tot = (long long)np * d;
+        scale_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, g_st>>>(gp->X.as<double>(), gp->ls.as<double>(), xf,
+                                                               gp->Xs.as<double>(), n, np, d);
+        LAUNCHED();
+    }
+    {
+        dim3 blk(32, 8), grd(np / 32, np / 32);
+        double* Kp = gp->K.as<double>();
+        const double* Xsp = gp->Xs.as<double>();
+        switch (cov_code(kern->family, kern->nu)) {
+            case 0: kbuild_kernel<0><<<grd, blk, 0, g_st>>>(Xsp, Kp, n, np, d, kern->const_value, jitter); break;
+            case 1: kbuild_kernel<1><<<grd, blk, 0, g_st>>>(Xsp, Kp, n, np, d, kern->const_value, jitter); break;
+            case 2: kbuild_kernel<2><<<grd, blk, 0, g_st>>>(Xsp, Kp, n, np, d, kern->const_value, jitter); break;
+            default: kbuild_kernel<3><<<grd, blk, 0, g_st>>>(Xsp, Kp, n, np, d, kern->const_value, jitter); break;
+        }
+        LAUNCHED();
+    }
+    CU(cudaGetLastError());
+    if ((rc = run_factor(gp))) return rc;
+    int info = 0;
+    if ((rc = d2h(&info, gp->info.p, sizeof(int)))) return rc;
+    *info_out = info;
     return B200BO_OK;
 }
 
@@ -594,8 +679,6 @@ extern "C" int b200bo_gp_fit(b200bo_gp* gp, const double* X, const double* y, in
         if (info) *info = finfo;
         return set_err(B200BO_ERR_NOT_PD, "%d-th leading minor of the array is not positive definite", finfo);
     }
-    if ((rc = transpose_W(gp))) return rc;
-    if ((rc = solve_alpha(gp))) return rc;
     if ((rc = sync_fit_stream())) return rc;
     gp->family = kern->family;
     gp->nu = kern->family == B200BO_KERNEL_RBF ? B200BO_NU_INF : kern->nu;
@@ -698,8 +781,6 @@ extern "C" int b200bo_gp_lml(b200bo_gp* gp, const b200bo_kernel* kern, double al
             for (int p = 0; p < ntheta; ++p) grad[p] = 0.0;
         return B200BO_OK;
     }
-    if ((rc = transpose_W(gp))) return rc;
-    if ((rc = solve_alpha(gp))) return rc;
     diag_kernel<<<(n + 255) / 256, 256, 0, g_st>>>(gp->L.as<double>(), np, gp->v1.as<double>(), n);
     LAUNCHED();
     std::vector<double> a(n), dg(n);

@@ -218,6 +218,17 @@ def to_b200_gp(gp, device=0, devices=None, precision="fp64"):
                                         **gp.get_params(deep=False))
 
 
+# restart-worker handles, shared per device (see fit); release_worker_pool() frees them
+_POOL_LOCK = threading.Lock()
+_POOLS = {}
+
+
+def release_worker_pool():
+    """Free the device memory held by the shared restart-worker handles (they are re-created on demand)."""
+    with _POOL_LOCK:
+        _POOLS.clear()
+
+
 class _Handle:
     """Owns one b200bo_gp*."""
 
@@ -444,20 +455,25 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
                                      "requires that all bounds are finite.")
                 for _ in range(self.n_restarts_optimizer):
                     starts.append(self._rng.uniform(bounds[:, 0], bounds[:, 1]))
+            # worker handles (5 N^2 doubles + a captured CUDA graph each) come from ONE pool per device shared by
+            # every GP of the process (target + constraint GPs fit one after the other), not one pool per GP
+            locked = _POOL_LOCK.acquire(blocking=False)
             try:
-                workers = self._restart_workers(len(starts), Xd, y, codes)
-            except B.B200Error:  # e.g. out of memory for the worker buffers: sequential loop
                 workers = None
-                L.b200bo_gp_set_private_stream(h.ptr, 0)
-            try:
+                if locked:
+                    try:
+                        workers = self._restart_workers(len(starts), Xd, y, codes)
+                    except B.B200Error:  # e.g. out of memory for the worker buffers: sequential loop
+                        _POOLS.pop(int(self.device), None)
+                        L.b200bo_gp_set_private_stream(h.ptr, 0)
                 if workers is None:
                     obj_func = make_obj(h)
                     optima = [self._constrained_optimization(obj_func, t0, bounds) for t0 in starts]
                 else:
                     optima = self._run_restarts_concurrently(workers, make_obj, starts, bounds)
             finally:
-                # worker handles hold 5 N^2 doubles each: never keep them between suggest() calls
-                self.__dict__.pop("_b200_restart_handles", None)
+                if locked:
+                    _POOL_LOCK.release()
             lml_values = list(map(itemgetter(1), optima))
             self.kernel_.theta = optima[np.argmin(lml_values)][0]
             self.kernel_._check_bounds_params()
@@ -504,7 +520,7 @@ class B200GaussianProcessRegressor(GaussianProcessRegressor):
         if (n_workers - 1) * 5 * 8 * npad * npad > self._RESTART_POOL_BYTES:
             return None
         L = B.lib()
-        pool = self.__dict__.setdefault("_b200_restart_handles", [])
+        pool = _POOLS.setdefault(int(self.device), [])
         while len(pool) < n_workers - 1:
             pool.append(_Handle(self.device))
         handles = [self._handle()] + pool[:n_workers - 1]
