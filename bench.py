@@ -394,6 +394,7 @@ def main():
 
         total_ms, kernel_ms, launches, clocks = timed(step_device, steps, warmup, sample_clocks)
         m_step = world * m_local if cfg["scaling"] == "weak" else cfg["m_total"]
+        step_device(0)  # untimed: the reported result is always that of candidate buffer 0 (comparable across legs / N)
         res = merged_result(sel, gathered)
         out = {"value": m_step * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps, "kernel_ms": float(np.mean(kernel_ms)),
                "launches": int(launches), "clocks": clocks, "result": {"argmin_index": res[0], "argmin_value": res[1],
