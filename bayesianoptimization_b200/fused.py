@@ -349,6 +349,132 @@ class _LockstepEvaluator:
                 self._flush()
 
 
+def _batched_lbfgsb(acq, seeds, bounds, maxcor=10, ftol=2.2204460492503131e-09, gtol=1e-5, eps=1e-8,
+                    maxfun=15000, maxiter=15000, maxls=20):
+    """All L-BFGS-B runs of ``_smart_minimize`` advanced TOGETHER by one Python thread around SciPy's own
+    compiled core (``scipy.optimize._lbfgsb.setulb``): the driver loop of ``_minimize_lbfgsb``
+    (SP/optimize/_lbfgsb_py.py:290-420: task handling, iteration / evaluation limits, warnflag -> success) and the
+    2-point gradient of ``ScalarFunction`` (f(x) then (f(x + h_i e_i) - f(x)) / ((x_i + h_i) - x_i) with h from
+    SciPy's ``_adjust_scheme_to_bounds``) are restated for S runs at once, so a round costs ONE device call of
+    S*(d+1) rows and ~0.1 ms of host time instead of S Python optimiser frames taking turns on the GIL
+    (measured: 2.4 ms per round for 10 runs).  Same core, same arithmetic, same iterates: x, fun, nit, nfev, status
+    and success equal ``scipy.optimize.minimize(..., method="L-BFGS-B")`` bit for bit (tests/test_host_cpu.py).
+    Raises ImportError / AttributeError when SciPy's private pieces are not the ones this was written against
+    (the caller then uses the thread-per-run driver)."""
+    from scipy.optimize import OptimizeResult
+    from scipy.optimize import _lbfgsb_py as _sp
+
+    setulb = _sp._lbfgsb.setulb
+    int_dtype = np.int64 if _sp.HAS_ILP64 else np.int32
+    b = np.asarray(bounds, dtype=np.float64)
+    lb, ub = b[:, 0].copy(), b[:, 1].copy()
+    if (lb > ub).any():
+        raise ValueError("LBFGSB - one of the lower bounds is greater than an upper bound.")
+    n = lb.size
+    m = maxcor
+    factr = ftol / np.finfo(float).eps
+    nbd = np.zeros(n, dtype=int_dtype)
+    low_bnd, upper_bnd = np.zeros(n), np.zeros(n)
+    for i in range(n):
+        lo_f, hi_f = not np.isinf(lb[i]), not np.isinf(ub[i])
+        if lo_f:
+            low_bnd[i] = lb[i]
+        if hi_f:
+            upper_bnd[i] = ub[i]
+        nbd[i] = {(False, False): 0, (True, False): 1, (True, True): 2, (False, True): 3}[(lo_f, hi_f)]
+
+    class Run:
+        pass
+
+    n_dev = len(getattr(acq, "devices", [0]))
+    runs = []
+    for k, s in enumerate(seeds):
+        r = Run()
+        r.dev = k % n_dev  # SURVEY.md 8e: seed r -> GPU r mod G
+        r.x = np.array(np.clip(np.asarray(s, dtype=np.float64).ravel(), lb, ub), dtype=np.float64)
+        r.f = np.array(0.0, dtype=np.float64)
+        r.g = np.zeros(n, dtype=np.float64)
+        r.wa = np.zeros(2 * m * n + 5 * n + 11 * m * m + 8 * m, np.float64)
+        r.iwa = np.zeros(3 * n, dtype=int_dtype)
+        r.task = np.zeros(2, dtype=int_dtype)
+        r.ln_task = np.zeros(2, dtype=int_dtype)
+        r.lsave = np.zeros(4, dtype=int_dtype)
+        r.isave = np.zeros(44, dtype=int_dtype)
+        r.dsave = np.zeros(29, dtype=np.float64)
+        r.nit = r.nfev = r.njev = 0
+        r.xe = None  # point of the cached (f, g), as ScalarFunction memoises it
+        r.done = False
+        runs.append(r)
+
+    def evaluate_pending(pending):
+        """f and the 2-point gradient at r.x for every pending run: one batch of (d+1) rows per run."""
+        if n_dev > 1:
+            pending = sorted(pending, key=lambda r: r.dev)  # stable: rows of one device are contiguous
+        blocks = []
+        for r in pending:
+            x0 = r.x.copy()
+            pts = _predicted_stencil(x0, lb, ub, eps)
+            blocks.append((x0, pts))
+        rows = np.vstack([np.vstack([x0[None, :], pts]) for x0, pts in blocks])
+        if n_dev > 1:
+            counts = np.zeros(n_dev + 1, dtype=np.int64)
+            for r in pending:
+                counts[r.dev + 1] += 1 + n
+            ys = np.asarray(acq(rows, shard_offsets=np.cumsum(counts)), dtype=np.float64)
+        else:
+            ys = np.asarray(acq(rows), dtype=np.float64)
+        off = 0
+        for r, (x0, pts) in zip(pending, blocks):
+            f0 = float(ys[off])
+            idx = np.arange(n)
+            dx = pts[idx, idx] - x0                      # (x0_i + h_i) - x0_i, as SP/optimize/_numdiff.py forms it
+            r.g = (ys[off + 1:off + 1 + n] - f0) / dx
+            r.f = f0
+            r.xe = x0
+            r.nfev += 1 + n
+            r.njev += 1
+            off += 1 + n
+
+    evaluate_pending(runs)  # ScalarFunction.__init__ evaluates f and g at x0 before the first setulb call
+    active = list(runs)
+    while active:
+        pending = []
+        for r in active:
+            while True:
+                r.g = r.g.astype(np.float64)
+                setulb(m, r.x, low_bnd, upper_bnd, nbd, r.f, r.g, factr, gtol, r.wa, r.iwa, r.task, r.lsave,
+                       r.isave, r.dsave, maxls, r.ln_task)
+                if r.task[0] == 3:
+                    if r.xe is not None and np.array_equal(r.x, r.xe):
+                        continue  # fun_and_grad(x) at the memoised point: no new evaluation
+                    pending.append(r)
+                    break
+                if r.task[0] == 1:
+                    r.nit += 1
+                    if r.nit >= maxiter:
+                        r.task[0], r.task[1] = 5, 504
+                    elif r.nfev > maxfun:
+                        r.task[0], r.task[1] = 5, 502
+                    continue
+                r.done = True
+                break
+        if pending:
+            evaluate_pending(pending)
+        active = [r for r in active if not r.done]
+    out = []
+    for r in runs:
+        if r.task[0] == 4:
+            warnflag = 0
+        elif r.nfev > maxfun or r.nit >= maxiter:
+            warnflag = 1
+        else:
+            warnflag = 2
+        msg = _sp.status_messages[int(r.task[0])] + ": " + _sp.task_messages[int(r.task[1])]
+        out.append(OptimizeResult(fun=r.f, jac=r.g, nfev=r.nfev, njev=r.njev, nit=r.nit, status=warnflag, message=msg,
+                                  x=r.x, success=(warnflag == 0)))
+    return out
+
+
 def lockstep_lbfgsb(acq, x_seeds, bounds, lockstep=True):
     """``[minimize(acq, seed, bounds=bounds, method="L-BFGS-B") for seed in x_seeds]`` (the loop at
     R/bayes_opt/acquisition.py:365-366) with the runs advanced in lockstep.  B200BO_LOCKSTEP=0 (or a
@@ -363,6 +489,11 @@ def lockstep_lbfgsb(acq, x_seeds, bounds, lockstep=True):
             else:
                 out.append(minimize(acq, s, bounds=bounds, method="L-BFGS-B"))
         return out
+    if _workers_supported() and os.environ.get("B200BO_LBFGSB_DRIVER", "batched") == "batched":
+        try:
+            return _batched_lbfgsb(acq, seeds, bounds)
+        except (ImportError, AttributeError, KeyError, TypeError):
+            pass  # SciPy's private L-BFGS-B pieces differ from the ones the batched driver restates: thread driver
     ev = _LockstepEvaluator(acq, len(seeds))
     results, errors = [None] * len(seeds), [None] * len(seeds)
 

@@ -34,10 +34,12 @@ def O():
     return gp_oracle
 
 
-@pytest.fixture(params=["dmma", "dfma"])
+@pytest.fixture(params=["dmma", "dmma8", "dfma"])
 def impl(request, monkeypatch):
-    """Both GEMM inner-loop variants of the fused kernel (B200BO_PREDICT_IMPL, read per launch)."""
-    monkeypatch.setenv("B200BO_PREDICT_IMPL", request.param)
+    """The variants of the fused fp64 kernel (read per launch): DMMA with 16 warps (default), DMMA with 8 warps,
+    DFMA register tiles."""
+    monkeypatch.setenv("B200BO_PREDICT_IMPL", "dfma" if request.param == "dfma" else "dmma")
+    monkeypatch.setenv("B200BO_PREDICT_WARPS", "8" if request.param == "dmma8" else "16")
     return request.param
 
 

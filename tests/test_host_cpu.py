@@ -258,9 +258,12 @@ def test_shard_and_merge_selection(bo):
         assert list(top) == list(np.argsort(ys, kind="stable")[:k])
 
 
-def test_lockstep_lbfgsb_equals_sequential_runs(bo):
+@pytest.mark.parametrize("driver", ["batched", "threads"])
+def test_lockstep_lbfgsb_equals_sequential_runs(bo, monkeypatch, driver):
     """The n_smart L-BFGS-B runs advanced in lockstep (one batched objective call per round) follow
-    exactly the iterates of independent sequential runs (R/bayes_opt/acquisition.py:365-366)."""
+    exactly the iterates of independent sequential runs (R/bayes_opt/acquisition.py:365-366) - with the
+    single-thread driver around SciPy's compiled core (default) and with the thread-per-run driver."""
+    monkeypatch.setenv("B200BO_LBFGSB_DRIVER", driver)
     from scipy.optimize import minimize
 
     from bayesianoptimization_b200.fused import lockstep_lbfgsb as _lockstep_lbfgsb
@@ -281,6 +284,19 @@ def test_lockstep_lbfgsb_equals_sequential_runs(bo):
     assert len(calls) < n_seq / 5
     for a, c in zip(seq, lock):
         assert np.array_equal(a.x, c.x) and a.fun == c.fun and a.nit == c.nit and a.success == c.success
+        assert a.nfev == c.nfev and a.status == c.status and a.message == c.message and np.array_equal(a.jac, c.jac)
+    # seeds on the bounds, and an objective that turns NaN (runs that fail must fail the same way)
+    edge = np.vstack([np.zeros(4), np.ones(4), seeds[:2]])
+    for a, c in zip([minimize(acq, s, bounds=b, method="L-BFGS-B") for s in edge], _lockstep_lbfgsb(acq, edge, b)):
+        assert np.array_equal(a.x, c.x) and a.fun == c.fun and a.nit == c.nit
+
+    def nanny(x):
+        x = np.atleast_2d(x)
+        return np.where(x[:, 0] > 0.5, np.nan, (x ** 2).sum(1))
+
+    for a, c in zip([minimize(nanny, s, bounds=b, method="L-BFGS-B") for s in seeds], _lockstep_lbfgsb(nanny, seeds, b)):
+        assert a.success == c.success and a.nit == c.nit and a.message == c.message
+        assert np.array_equal(a.x, c.x, equal_nan=True)
 
     def bad(x):
         raise RuntimeError("boom")

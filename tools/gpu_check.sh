@@ -29,26 +29,37 @@ if [ "$mode" = "bench" ] || [ "$mode" = "all" ] || [ "$mode" = "fit" ]; then
   B200BO_GEMM=64 B200BO_POTRF=serial timeout 900 python tools/fit_bench.py > $out/fit_bench_gemm64.json 2> $out/fit_bench_gemm64.err; cat $out/fit_bench_gemm64.json
 fi
 if [ "$mode" = "prof" ]; then
-  echo "== ncu launch list"
+  # ncu reports are summarised ON the box (raw metric page as csv, gzip) and deleted: gpurun_out is capped at 64 MiB
+  summarise() { ncu -i $1.ncu-rep --page raw --csv 2>/dev/null | gzip > $1.raw.csv.gz; rm -f $1.ncu-rep; }
+  echo "== ncu launch list (default bench step, no extra legs)"
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches.csv \
-     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/bench_under_ncu.log 2>&1
-  echo "ncu exit $?"; wc -l $out/launches.csv
-  echo "== ncu full (predict kernel)"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:predict_acq_kernel -s 3 -c 1 -o $out/prof_predict -f \
-     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > $out/ncu_full.log 2>&1
-  echo "ncu full exit $?"
+     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > $out/bench_under_ncu.log 2>&1
+  echo "ncu exit $?"; wc -l $out/launches.csv; gzip -f $out/launches.csv
+  echo "== ncu full (fp64 predict kernels, 16 and 8 warps)"
+  timeout 900 ncu --set full --clock-control none -k regex:predict_acq16_kernel -s 3 -c 1 -o $out/prof_predict16 -f \
+     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > $out/ncu_full16.log 2>&1
+  echo "ncu full exit $?"; summarise $out/prof_predict16
+  B200BO_PREDICT_WARPS=8 timeout 900 ncu --set full --clock-control none -k regex:predict_acq_kernel -s 3 -c 1 -o $out/prof_predict8 -f \
+     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > $out/ncu_full8.log 2>&1
+  echo "ncu full exit $?"; summarise $out/prof_predict8
   echo "== ncu full (fp32-mode kernel)"
-  B200BO_PREDICT_IMPL=tf32 timeout 900 ncu --set full --clock-control none --import-source on -k regex:predict_acq_tc2 -s 3 -c 1 -o $out/prof_predict_tc2 -f \
+  B200BO_PREDICT_IMPL=tf32 timeout 900 ncu --set full --clock-control none -k regex:predict_acq_tc2 -s 3 -c 1 -o $out/prof_predict_tc2 -f \
      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > $out/ncu_full_tc2.log 2>&1
-  echo "ncu tc2 exit $?"
-  echo "== ncu launch list + full captures of the fit-side kernels (one LML+gradient evaluation, N=4096)"
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches_lml.csv python tools/lml_once.py > $out/lml_once.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:dgemm128 -s 130 -c 6 -o $out/prof_fit_gemm -f python tools/lml_once.py > $out/ncu_fit_gemm.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"potrf_diag|lml_grad|kbuild" -s 66 -c 4 -o $out/prof_fit_misc -f python tools/lml_once.py > $out/ncu_fit_misc.log 2>&1
+  echo "ncu tc2 exit $?"; summarise $out/prof_predict_tc2
+  echo "== launch list + full captures of the fit-side kernels (one fit + one LML+gradient evaluation, N=4096; graph off)"
+  B200BO_GRAPH=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches_lml.csv python tools/lml_once.py > $out/lml_once.log 2>&1
+  gzip -f $out/launches_lml.csv
+  B200BO_GRAPH=0 timeout 900 ncu --set full --clock-control none -k regex:dgemm128 -s 130 -c 8 -o $out/prof_fit_gemm -f python tools/lml_once.py > $out/ncu_fit_gemm.log 2>&1
+  summarise $out/prof_fit_gemm
+  B200BO_GRAPH=0 timeout 900 ncu --set full --clock-control none -k regex:"potrf_diag|lml_grad|kbuild" -s 66 -c 4 -o $out/prof_fit_misc -f python tools/lml_once.py > $out/ncu_fit_misc.log 2>&1
+  summarise $out/prof_fit_misc
   echo "ncu fit exit $?"
   echo "== ncu launch list of one suggest() without refit (small-batch kernels)"
   REPS=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches_suggest.csv python tools/suggest_once.py > $out/suggest_once.log 2>&1
-  tail -2 $out/suggest_once.log
+  tail -2 $out/suggest_once.log; gzip -f $out/launches_suggest.csv
+  echo "== timings without profiler: LML (graph on/off), suggest"
+  python tools/lml_time.py > $out/lml_time.json 2>&1; cat $out/lml_time.json
+  REPS=3 python tools/suggest_once.py > $out/suggest_time.log 2>&1; cat $out/suggest_time.log
 fi
 if [ "$mode" = "variants" ]; then
   for w in 8 16; do
