@@ -103,7 +103,7 @@ struct b200bo_gp {
     // predict-side scratch (used when this handle is gps[0] of a call)
     DevBuf pscratch, xc, out_acq, out_mu, out_sd, sel, clamp;
     // small-batch path scratch (per GP) + work-unit tables (rebuilt when np changes)
-    DevBuf s_ksm, s_partial, s_mupart, s_unit, s_rb;
+    DevBuf s_ksm, s_partial, s_mupart, s_unit, s_rb, s_colsq;
     int s_np = 0, s_nunits = 0;
     // fp32 mode: L^-1 as tf32 (hi,lo) UMMA operand images (built on first use after a fit)
     DevBuf tc_linv;
@@ -199,6 +199,7 @@ static int init_handle(b200bo_gp* gp) {
                             kPredictSmemBytesTc));
     CU(cudaFuncSetAttribute(predict_acq_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             kPredictSmemBytesTc2));
+    CU(cudaFuncSetAttribute(small_trsv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallTrsvSmemBytes));
     CU(cudaFuncSetAttribute(predict_acq16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDmma));
     CU(cudaFuncSetAttribute(predict_acq16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDmma));
     CU(cudaFuncSetAttribute(dgemm128_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemm128SmemBytes));
@@ -236,7 +237,7 @@ extern "C" void b200bo_gp_destroy(b200bo_gp* gp) {
     DevBuf* bufs[] = {&gp->X, &gp->Xs, &gp->y, &gp->K, &gp->L, &gp->W, &gp->WT, &gp->T,
                       &gp->alphav, &gp->v1, &gp->v2, &gp->ls, &gp->xf, &gp->info, &gp->part,
                       &gp->pscratch, &gp->xc, &gp->out_acq, &gp->out_mu, &gp->out_sd, &gp->sel,
-                      &gp->clamp, &gp->s_ksm, &gp->s_partial, &gp->s_mupart, &gp->s_unit, &gp->s_rb,
+                      &gp->clamp, &gp->s_ksm, &gp->s_partial, &gp->s_mupart, &gp->s_unit, &gp->s_rb, &gp->s_colsq,
                       &gp->tc_linv, &gp->cov_xc, &gp->cov_kst, &gp->cov_v, &gp->cov_c, &gp->cov_out, &gp->cov_mu,
                       &gp->sel_cta, &gp->pbounds, &gp->prow, &gp->pside};
     for (DevBuf* b : bufs) b->release();
@@ -401,14 +402,15 @@ static int ensure_bulk_stream(b200bo_gp* gp) {
 template <bool TA, bool TB>
 static int gemm(int M, int N, int K, double alpha, const double* A, int lda, long long sA,
                 const double* B, int ldb, long long sB, double beta, double* C, int ldc,
-                long long sC, int batch, int lower_only, int kmode, int skip = 0, const cudaStream_t* stp = nullptr) {
+                long long sC, int batch, int lower_only, int kmode, int skip = 0, const cudaStream_t* stp = nullptr,
+                double* side = nullptr) {
     if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return B200BO_OK;
     const cudaStream_t st = stp ? *stp : g_st;
     // 128x128 pipelined tiles wherever a tile can be filled; the 64x64 kernel for narrow panels / small blocks
     if (M >= 128 && N >= 128 && !gemm_force64()) {
         dim3 grid((N + 127) / 128, (M + 127) / 128, batch);
         dgemm128_kernel<TA, TB><<<grid, 256, kGemm128SmemBytes, st>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta,
-                                                                      C, ldc, sC, lower_only, kmode, skip);
+                                                                      C, ldc, sC, lower_only, kmode, skip, side);
     } else {
         dim3 grid(N / 64, M / 64, batch);
         dgemm64_kernel<TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC,
@@ -472,32 +474,38 @@ static int factor_body(b200bo_gp* gp) {
         // panel solve, and the bulk trailing update leaves block (j+1, j+1) alone.  Every value is produced by
         // exactly one kernel: the result does not depend on how the two streams interleave.
         const cudaStream_t sb = gp->bulk_stream;
-        double* Pside = gp->pside.as<double>();
+        // A[j+1, j] as it is BEFORE the bulk panel solve of panel j overwrites it in place: produced by the trailing
+        // update of panel j-1 (its epilogue stores that block a second time, densely), double-buffered by step parity
+        double* Pside[2] = {gp->pside.as<double>(), gp->pside.as<double>() + 64 * 64};
         CU(cudaEventRecord(gp->ev_chain, g_st));
         CU(cudaStreamWaitEvent(sb, gp->ev_chain, 0));  // K build / copies issued so far
+        copy_block64_kernel<<<1, 256, 0, sb>>>(L + (size_t)64 * np, np, Pside[1]);  // A[1, 0]: no earlier panel touches it
+        LAUNCHED();
+        CU(cudaEventRecord(gp->ev_bulk, sb));
         potrf_diag_kernel<<<1, 256, kPotrfSmemBytes, g_st>>>(L, np, 0, W, np, gp->info.as<int>(), nullptr, nullptr, 0);
         LAUNCHED();
         CU(cudaEventRecord(gp->ev_chain, g_st));
-        for (int j0 = 0; j0 + 64 < np; j0 += 64) {
+        for (int j0 = 0, j = 0; j0 + 64 < np; j0 += 64, ++j) {
             const int below = np - j0 - 64;
             double* panel = L + (size_t)(j0 + 64) * np + j0;  // rows below the diagonal block, columns of panel j
             const double* Dj = W + (size_t)j0 * np + j0;
-            CU(cudaStreamWaitEvent(sb, gp->ev_chain, 0));  // inv(L_jj) is ready (and the chain is done with Pside)
-            copy_block64_kernel<<<1, 256, 0, sb>>>(panel, np, Pside);
-            LAUNCHED();
-            CU(cudaEventRecord(gp->ev_bulk, sb));
-            if ((rc = gemm<false, true>(below, 64, 64, 1.0, panel, np, 0, Dj, np, 0, 0.0, panel, np, 0, 1, 0, 0, 0, &sb)))
-                return rc;
-            // chain: diagonal block j+1 (its A[j+1, j+1] holds the updates of panels < j: the bulk stream has finished them)
+            // chain: diagonal block j+1.  Its inputs: Pside[(j+1)&1] (written by the trailing update of panel j-1, or the
+            // initial copy) and A[j+1, j+1] with the updates of panels < j - both complete when ev_bulk (recorded after
+            // that trailing update) has fired; inv(L_jj) comes from the previous kernel of this stream.
             CU(cudaStreamWaitEvent(g_st, gp->ev_bulk, 0));
             potrf_diag_kernel<<<1, 256, kPotrfSmemBytes, g_st>>>(L, np, j0 + 64, W + (size_t)(j0 + 64) * np + j0 + 64, np,
-                                                           gp->info.as<int>(), Pside, Dj, np);
+                                                           gp->info.as<int>(), Pside[(j + 1) & 1], Dj, np);
             LAUNCHED();
-            CU(cudaEventRecord(gp->ev_chain, g_st));
-            // bulk: trailing update of panel j on everything but block (j+1, j+1)
-            if ((rc = gemm<false, true>(below, below, 64, -1.0, panel, np, 0, panel, np, 0, 1.0,
-                                        L + (size_t)(j0 + 64) * np + j0 + 64, np, 0, 1, 1, 0, 64, &sb)))
+            // bulk: panel solve (needs inv(L_jj): ev_chain of the PREVIOUS chain kernel), then the trailing update of
+            // panel j on everything but block (j+1, j+1); it also leaves A[j+2, j+1] in Pside[j&1] for the next step
+            CU(cudaStreamWaitEvent(sb, gp->ev_chain, 0));
+            CU(cudaEventRecord(gp->ev_chain, g_st));  // re-recorded AFTER the wait above was enqueued: now marks step j+1
+            if ((rc = gemm<false, true>(below, 64, 64, 1.0, panel, np, 0, Dj, np, 0, 0.0, panel, np, 0, 1, 0, 0, 0, &sb)))
                 return rc;
+            if ((rc = gemm<false, true>(below, below, 64, -1.0, panel, np, 0, panel, np, 0, 1.0,
+                                        L + (size_t)(j0 + 64) * np + j0 + 64, np, 0, 1, 1, 0, 64, &sb, Pside[j & 1])))
+                return rc;
+            CU(cudaEventRecord(gp->ev_bulk, sb));
         }
         CU(cudaEventRecord(gp->ev_bulk, sb));
         CU(cudaStreamWaitEvent(g_st, gp->ev_bulk, 0));
@@ -550,7 +558,7 @@ static int factor_body(b200bo_gp* gp) {
 static int run_factor(b200bo_gp* gp) {
     int rc;
     if ((rc = ensure_bulk_stream(gp))) return rc;
-    if ((rc = gp->pside.reserve(sizeof(double) * 64 * 64))) return rc;
+    if ((rc = gp->pside.reserve(sizeof(double) * 2 * 64 * 64))) return rc;
     const char* ge = getenv("B200BO_GRAPH");
     if (ge && ge[0] == '0') return factor_body(gp);
     const unsigned long long key[] = {(unsigned long long)gp->np, (unsigned long long)gp->K.p, (unsigned long long)gp->L.p,
@@ -904,6 +912,7 @@ static int ensure_small(b200bo_gp* gp) {
     if ((rc = gp->s_ksm.reserve(sizeof(double) * (size_t)SMAXP * np * SMC))) return rc;
     if ((rc = gp->s_partial.reserve(sizeof(double) * (size_t)SMAXP * units.size() * SROWS * SMC))) return rc;
     if ((rc = gp->s_mupart.reserve(sizeof(double) * (size_t)SMAXP * (np / 128) * SMC))) return rc;
+    if ((rc = gp->s_colsq.reserve(sizeof(double) * (size_t)SMAXP * (np / SROWS) * SMC))) return rc;
     CU(cudaMemcpy(gp->s_unit.p, units.data(), sizeof(int2) * units.size(), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(gp->s_rb.p, rbs.data(), sizeof(int2) * rbs.size(), cudaMemcpyHostToDevice));
     gp->s_np = np;
@@ -1084,6 +1093,7 @@ static int eval_core(const b200bo_acq* spec, const CandSrc& src, int64_t m, doub
             S.sg[g].ksm = gp->s_ksm.as<double>();
             S.sg[g].partial = gp->s_partial.as<double>();
             S.sg[g].mu_part = gp->s_mupart.as<double>();
+            S.sg[g].colsq_rb = gp->s_colsq.as<double>();
             S.sg[g].unit_tab = gp->s_unit.as<int2>();
             S.sg[g].rb_tab = gp->s_rb.as<int2>();
             S.nunits[g] = gp->s_nunits;
@@ -1095,12 +1105,14 @@ static int eval_core(const b200bo_acq* spec, const CandSrc& src, int64_t m, doub
             const long long left = m - c0;
             const int npass = (int)((left + SMC - 1) / SMC < SMAXP ? (left + SMC - 1) / SMC : SMAXP);
             for (int g = 0; g < spec->n_gps; ++g) {
-                small_kstar_kernel<<<dim3(spec->gps[g]->np / 128, npass), 128, 0, stream>>>(S, g);
-                small_trsv_kernel<<<dim3(spec->gps[g]->s_nunits, npass), 256, 0, stream>>>(S, g);
+                small_kstar_kernel<<<dim3(spec->gps[g]->np / 128, npass), 256, 0, stream>>>(S, g);
+                small_trsv_kernel<<<spec->gps[g]->s_nunits, 256, kSmallTrsvSmemBytes, stream>>>(S, g, npass);
+                small_reduce_kernel<<<dim3(spec->gps[g]->np / SROWS, npass), 256, 0, stream>>>(S, g);
+                LAUNCHED();
                 LAUNCHED();
                 LAUNCHED();
             }
-            small_finish_kernel<<<npass, 1024, 0, stream>>>(S);
+            small_finish_kernel<<<npass, 256, 0, stream>>>(S);
             LAUNCHED();
         }
         CU(cudaGetLastError());

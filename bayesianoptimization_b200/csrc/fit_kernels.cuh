@@ -219,9 +219,23 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256, 1)
 dgemm128_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int lda, long long sA,
                 const double* __restrict__ B, int ldb, long long sB, double beta, double* C, int ldc,
-                long long sC, int lower_only, int kmode, int skip) {
+                long long sC, int lower_only, int kmode, int skip, double* __restrict__ side) {
     extern __shared__ __align__(16) double g128_smem[];
-    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
+    // tile order: heaviest tiles first.  With triangular k-ranges (kmode) a tile's work is proportional to its
+    // k-length; blocks are dispatched in linear order, and a full-length tile that starts in the second wave
+    // determines the duration of the launch.
+    int bx = blockIdx.x, by = blockIdx.y;
+    {
+        const int lin = blockIdx.y * gridDim.x + blockIdx.x;
+        if (kmode == 2) {          // k in [n0, K): small n0 = heavy -> n-tiles become the slow index
+            bx = lin / gridDim.y;
+            by = lin % gridDim.y;
+        } else if (kmode == 1) {   // k in [0, m0 + 128): large m0 = heavy -> descending m-tiles, slow index
+            by = gridDim.y - 1 - lin / gridDim.x;
+            bx = lin % gridDim.x;
+        }
+    }
+    const int m0 = by * 128, n0 = bx * 128;
     if (lower_only && n0 > m0) return;
     A += (long long)blockIdx.z * sA;
     B += (long long)blockIdx.z * sB;
@@ -303,6 +317,9 @@ dgemm128_kernel(int M, int N, int K, double alpha, const double* __restrict__ A,
                 v.y = fma(beta, o.y, v.y);
             }
             *c = v;
+            // look-ahead Cholesky: the updated block (rows 64..127, columns 0..63 of C) is also stored densely in
+            // `side` - it is what the NEXT diagonal kernel needs before the bulk panel solve overwrites it in place
+            if (side && m >= 64 && m < 128 && n < 64) *reinterpret_cast<double2*>(side + (size_t)(m - 64) * 64 + n) = v;
         }
     }
 }
@@ -340,30 +357,53 @@ potrf_diag_kernel(double* A, int ld, int j0, double* Dinv, int ldd, int* info, c
     }
     __syncthreads();
     if (Pprev) {
-        const int c = tid & 63, r0 = (tid >> 6) * 16;
-        double xv[16];
+        // 4x4 register tiles: thread (ti, tj) owns rows 4ti..4ti+3, columns 4tj..4tj+3 (8 shared loads per 16 FMAs)
+        const int tj = tid & 15, ti = tid >> 4;
+        double acc[4][4];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) xv[q] = 0.0;
-        for (int k = 0; k <= c; ++k) {  // Dprev is lower triangular: D[c][k] = 0 for k > c
-            const double dck = T[c * kLd + k];
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int q = 0; q < 16; ++q) xv[q] = fma(V[(r0 + q) * kLd + k], dck, xv[q]);
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        const int kmax = 4 * tj + 3;  // Dprev is lower triangular: D[c][k] = 0 for k > c
+        for (int k = 0; k <= kmax; ++k) {
+            double p[4], dd[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) p[i] = V[(4 * ti + i) * kLd + k];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dd[j] = T[(4 * tj + j) * kLd + k];  // zero above the diagonal (loaded so)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(p[i], dd[j], acc[i][j]);
         }
         __syncthreads();
 #pragma unroll
-        for (int q = 0; q < 16; ++q) V[(r0 + q) * kLd + c] = xv[q];
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) V[(4 * ti + i) * kLd + 4 * tj + j] = acc[i][j];  // X over P
         __syncthreads();
-        double sv[16];
+        if (tj <= ti) {  // lower tiles of S -= X X^T
 #pragma unroll
-        for (int q = 0; q < 16; ++q) sv[q] = 0.0;
-        for (int k = 0; k < kB; ++k) {
-            const double xck = V[c * kLd + k];
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int q = 0; q < 16; ++q) sv[q] = fma(V[(r0 + q) * kLd + k], xck, sv[q]);
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+            for (int k = 0; k < kB; ++k) {
+                double xr[4], xc[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xr[i] = V[(4 * ti + i) * kLd + k];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xc[j] = V[(4 * tj + j) * kLd + k];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fma(xr[i], xc[j], acc[i][j]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (4 * tj + j <= 4 * ti + i) S[(4 * ti + i) * kLd + 4 * tj + j] -= acc[i][j];
         }
-#pragma unroll
-        for (int q = 0; q < 16; ++q)
-            if (c <= r0 + q) S[(r0 + q) * kLd + c] -= sv[q];
         __syncthreads();
         for (int idx = tid; idx < kB * kB; idx += kThreads) V[(idx >> 6) * kLd + (idx & 63)] = 0.0;
         __syncthreads();

@@ -1083,6 +1083,7 @@ struct SmallGp {
     double* ksm;            // [np][SMC]
     double* partial;        // [nunits][SROWS][SMC]
     double* mu_part;        // [np/128][SMC]
+    double* colsq_rb;       // [np/SROWS][SMC] per pass: sum over the rows of a row block of V^2
     const int2* unit_tab;   // [nunits] (row-block, k-chunk)
     const int2* rb_tab;     // [np/SROWS] (first unit, number of units)
 };
@@ -1106,18 +1107,21 @@ __device__ __forceinline__ int small_pass_mc(const SmallParams& S, int pass) {
     return (int)(left < SMC ? (left < 0 ? 0 : left) : SMC);
 }
 
-__global__ void __launch_bounds__(128)
+// K*[k][c] for one block of 128 training rows and one pass of 32 candidates (blockIdx.y = pass): thread =
+// (candidate c, group of 16 rows); the training row is a warp-wide broadcast load, K* rows are written as
+// coalesced 256-byte segments; per-candidate partial of K* alpha_ over the block in a fixed order.
+__global__ void __launch_bounds__(256)
 small_kstar_kernel(const SmallParams S, int g) {
     const GpDev& G = S.P.gp[g];
     const SmallGp& Q = S.sg[g];
-    __shared__ double xc_s[SMC * B200BO_MAX_DIM];
-    __shared__ double wsum[4][SMC];
+    __shared__ double xc_s[SMC][B200BO_MAX_DIM + 1];
+    __shared__ double wsum[8][SMC];
     const int tid = threadIdx.x, d = S.P.d;
     const int pass = blockIdx.y, mc = small_pass_mc(S, pass);
     const long long pc0 = small_pass_c0(S, pass);
     double* ksm = Q.ksm + (size_t)pass * G.np * SMC;
     double* mu_part = Q.mu_part + (size_t)pass * (G.np / 128) * SMC;
-    for (int idx = tid; idx < SMC * d; idx += 128) {
+    for (int idx = tid; idx < SMC * d; idx += 256) {
         const int c = idx / d, j = idx - c * d;
         double v = 0.0;
         if (c < mc) {
@@ -1125,109 +1129,165 @@ small_kstar_kernel(const SmallParams S, int g) {
             if (G.xform && G.xform[j] == B200BO_XFORM_ROUND) v = rint(v);
             v = v / G.ls[j];
         }
-        xc_s[idx] = v;
+        xc_s[c][j] = v;
     }
     __syncthreads();
-    const int n = blockIdx.x * 128 + tid;
-    const double* xr = G.Xs + (size_t)n * d;
-    const double an = G.alphav[n];
-    for (int c = 0; c < SMC; ++c) {
+    const int c = tid & 31, rg = tid >> 5;
+    double mu_acc = 0.0;
+    for (int q = 0; q < 16; ++q) {
+        const int n = blockIdx.x * 128 + rg * 16 + q;
         double kv = 0.0;
         if (c < mc && n < G.n) {
+            const double* xr = G.Xs + (size_t)n * d;
             double r2 = 0.0;
             for (int j = 0; j < d; ++j) {
-                const double df = xc_s[c * d + j] - xr[j];
+                const double df = xc_s[c][j] - xr[j];
                 r2 = fma(df, df, r2);
             }
             kv = G.constv * cov_from_r2(r2, G.family, G.nu);
         }
         ksm[(size_t)n * SMC + c] = kv;
-        double t = an * kv;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if ((tid & 31) == 0) wsum[tid >> 5][c] = t;
+        mu_acc = fma(G.alphav[n], kv, mu_acc);
     }
+    wsum[rg][c] = mu_acc;
     __syncthreads();
-    if (tid < SMC)
-        mu_part[(size_t)blockIdx.x * SMC + tid] = ((wsum[0][tid] + wsum[1][tid]) + wsum[2][tid]) + wsum[3][tid];
+    if (tid < SMC) {
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += wsum[r][tid];
+        mu_part[(size_t)blockIdx.x * SMC + tid] = t;
+    }
 }
 
+// Partial V for one work unit (64 rows x <= 512 k) and ALL passes of the launch group: the W tile is staged once
+// per k sub-tile and used for every pass (the passes used to be separate CTAs that each re-read L^-1).
+constexpr int kSmallTrsvSmemBytes = (SROWS * SWSTR + SMAXP * SKT * SMC) * 8;  // 82944
 __global__ void __launch_bounds__(256)
-small_trsv_kernel(const SmallParams S, int g) {
+small_trsv_kernel(const SmallParams S, int g, int npass) {
     const GpDev& G = S.P.gp[g];
     const SmallGp& Q = S.sg[g];
-    __shared__ __align__(16) double Wt[SROWS * SWSTR];
-    __shared__ __align__(16) double Kt[SKT * SMC];
+    extern __shared__ __align__(16) double strsv_smem[];
+    double* Wt = strsv_smem;                  // [SROWS][SWSTR]
+    double* Kt = strsv_smem + SROWS * SWSTR;  // [npass][SKT][SMC]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pass = blockIdx.y;
-    const double* ksm = Q.ksm + (size_t)pass * G.np * SMC;
     const int2 u = Q.unit_tab[blockIdx.x];
     const int r0 = u.x * SROWS;
     const int kbeg = u.y * SKCH;
     const int kend = min(kbeg + SKCH, r0 + SROWS);
     const int np = G.np;
-    double acc[8];
+    double acc[SMAXP][8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+    for (int p = 0; p < SMAXP; ++p)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[p][q] = 0.0;
     for (int k0 = kbeg; k0 < kend; k0 += SKT) {
         for (int idx = tid; idx < SROWS * SKT; idx += 256) {
             const int r = idx / SKT, kk = idx % SKT;
             Wt[r * SWSTR + kk] = Q.W[(size_t)(r0 + r) * np + k0 + kk];
         }
-        for (int idx = tid; idx < SKT * SMC; idx += 256) Kt[idx] = ksm[(size_t)k0 * SMC + idx];
+        for (int p = 0; p < npass; ++p) {
+            const double* ksm = Q.ksm + (size_t)p * np * SMC + (size_t)k0 * SMC;
+            for (int idx = tid; idx < SKT * SMC; idx += 256) Kt[p * SKT * SMC + idx] = ksm[idx];
+        }
         __syncthreads();
-#pragma unroll 4
+#pragma unroll 2
         for (int kk = 0; kk < SKT; kk += 2) {
-            const double k0v = Kt[kk * SMC + lane], k1v = Kt[(kk + 1) * SMC + lane];
+            double2 w[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const double2 w = *reinterpret_cast<const double2*>(&Wt[(warp * 8 + q) * SWSTR + kk]);
-                acc[q] = fma(w.x, k0v, acc[q]);
-                acc[q] = fma(w.y, k1v, acc[q]);
+            for (int q = 0; q < 8; ++q) w[q] = *reinterpret_cast<const double2*>(&Wt[(warp * 8 + q) * SWSTR + kk]);
+#pragma unroll
+            for (int p = 0; p < SMAXP; ++p) {
+                if (p < npass) {
+                    const double k0v = Kt[p * SKT * SMC + kk * SMC + lane], k1v = Kt[p * SKT * SMC + (kk + 1) * SMC + lane];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        acc[p][q] = fma(w[q].x, k0v, acc[p][q]);
+                        acc[p][q] = fma(w[q].y, k1v, acc[p][q]);
+                    }
+                }
             }
         }
         __syncthreads();
     }
-    double* out = Q.partial + ((size_t)pass * S.nunits[g] + blockIdx.x) * SROWS * SMC;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) out[(warp * 8 + q) * SMC + lane] = acc[q];
+    for (int p = 0; p < SMAXP; ++p) {
+        if (p < npass) {
+            double* out = Q.partial + ((size_t)p * S.nunits[g] + blockIdx.x) * SROWS * SMC;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) out[(warp * 8 + q) * SMC + lane] = acc[p][q];
+        }
+    }
 }
 
-__global__ void __launch_bounds__(1024)
+// Per (row block of 64 rows, pass): sum the k-chunk partials of every row in a fixed order, square, and reduce the
+// 64 rows -> colsq_rb[pass][row block][candidate].  grid (np / 64, npass).
+__global__ void __launch_bounds__(256)
+small_reduce_kernel(const SmallParams S, int g) {
+    const GpDev& G = S.P.gp[g];
+    const SmallGp& Q = S.sg[g];
+    __shared__ double red[8][SMC];
+    const int tid = threadIdx.x, c = tid & 31, rg = tid >> 5;
+    const int pass = blockIdx.y;
+    const int2 rb = Q.rb_tab[blockIdx.x];
+    const double* partial = Q.partial + (size_t)pass * S.nunits[g] * SROWS * SMC;
+    double s = 0.0;
+    for (int q = 0; q < 8; ++q) {
+        const int r = rg * 8 + q;
+        double v = 0.0;
+        for (int j = 0; j < rb.y; ++j) v += partial[((size_t)(rb.x + j) * SROWS + r) * SMC + c];
+        s = fma(v, v, s);
+    }
+    red[rg][c] = s;
+    __syncthreads();
+    if (tid < SMC) {
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += red[r][tid];
+        Q.colsq_rb[((size_t)pass * (G.np / SROWS) + blockIdx.x) * SMC + tid] = t;
+    }
+}
+
+// Per pass (blockIdx.x): sum the row-block and K* alpha_ partials in index order, then the per-candidate epilogue
+// of every GP.  256 threads = 32 candidates x 8 slices of the partial lists (fixed-order two-level sum).
+__global__ void __launch_bounds__(256)
 small_finish_kernel(const SmallParams S) {
-    __shared__ double red[32][SMC + 1];
+    __shared__ double red[8][SMC];
     __shared__ double colsq_s[B200BO_MAX_GPS][SMC];
     __shared__ double mu_s[B200BO_MAX_GPS][SMC];
-    const int tid = threadIdx.x, c = tid & 31, rg = tid >> 5;
+    const int tid = threadIdx.x, c = tid & 31, sl = tid >> 5;
     const int pass = blockIdx.x, mc = small_pass_mc(S, pass);
     const long long pc0 = small_pass_c0(S, pass);
     for (int g = 0; g < S.P.n_gps; ++g) {
         const GpDev& G = S.P.gp[g];
         const SmallGp& Q = S.sg[g];
-        const double* partial = Q.partial + (size_t)pass * S.nunits[g] * SROWS * SMC;
-        const double* mu_part = Q.mu_part + (size_t)pass * (G.np / 128) * SMC;
+        const int nrb = G.np / SROWS, nb = G.np / 128;
+        const double* crb = Q.colsq_rb + (size_t)pass * nrb * SMC;
+        const double* mu_part = Q.mu_part + (size_t)pass * nb * SMC;
+        // slice sl sums a contiguous range of the lists; the 8 slice sums are then added in order
         double s = 0.0;
-        for (int row = rg; row < G.np; row += 32) {
-            const int2 rb = Q.rb_tab[row / SROWS];
-            const int r = row % SROWS;
-            double v = 0.0;
-            for (int j = 0; j < rb.y; ++j) v += partial[((size_t)(rb.x + j) * SROWS + r) * SMC + c];
-            s = fma(v, v, s);
-        }
-        red[rg][c] = s;
+        for (int b = sl * ((nrb + 7) / 8); b < min(nrb, (sl + 1) * ((nrb + 7) / 8)); ++b) s += crb[(size_t)b * SMC + c];
+        red[sl][c] = s;
         __syncthreads();
-        if (rg == 0) {
+        if (sl == 0) {
             double t = 0.0;
-            for (int r = 0; r < 32; ++r) t += red[r][c];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) t += red[r][c];
             colsq_s[g][c] = t;
-            double m = 0.0;
-            const int nb = G.np / 128;
-            for (int b = 0; b < nb; ++b) m += mu_part[(size_t)b * SMC + c];
-            mu_s[g][c] = m;
+        }
+        __syncthreads();
+        s = 0.0;
+        for (int b = sl * ((nb + 7) / 8); b < min(nb, (sl + 1) * ((nb + 7) / 8)); ++b) s += mu_part[(size_t)b * SMC + c];
+        red[sl][c] = s;
+        __syncthreads();
+        if (sl == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) t += red[r][c];
+            mu_s[g][c] = t;
         }
         __syncthreads();
     }
-    if (rg == 0 && c < mc) {
+    if (sl == 0 && c < mc) {
         double base_neg = 0.0, prod = 1.0;
         for (int g = 0; g < S.P.n_gps; ++g)
             candidate_epilogue(S.P, S.P.gp[g], g, mu_s[g][c], colsq_s[g][c], pc0 + c, base_neg, prod);
