@@ -68,9 +68,15 @@ def test_single_process_devices_equal_one_device(bo, precision):
         got = fg.argmin_topk(xt, 10)
         assert got[0] == one[0] and got[1] == one[1] and list(got[2]) == list(one[2]), (g, got, one)
         assert np.array_equal(fg(xt), ys)                       # even split
-        off = np.array([0, 10, 10] + [len(xt)] * (g - 2))[: g + 1]
-        off[-1] = len(xt)
-        assert np.array_equal(fg(xt, shard_offsets=off), ys)    # ragged split incl. an empty shard
+        # ragged split incl. an empty shard, as the L-BFGS-B driver issues it (seed r's rows on device r mod G): inside
+        # an optimiser run the kernel choice is a function of the model only (PATH_STABLE), so a row's value does not
+        # depend on the shard - or the device - it lands in
+        xs = xt[:333]
+        off = np.array([0, 10, 10] + [len(xs)] * (g - 2))[: g + 1]
+        off[-1] = len(xs)
+        with f1.refine_mode(), fg.refine_mode():
+            assert np.array_equal(fg(xs, shard_offsets=off), f1(xs))
+            assert np.array_equal(fg(xs), f1(xs))
         tiny = fg.argmin_topk(xt[:1], 3)                        # fewer rows than devices
         assert tiny[0] == 0 and list(tiny[2]) == [0]
         # throughput mode: rows depend on (seed, global index) only
