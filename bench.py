@@ -568,7 +568,8 @@ def report(args, world, cfg, leg, extra, fitleg, X, y):
             "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
             "frac_of_40tf_fallback": ach_tf / 40.0,
             "traffic": traffic, "traffic_source": traffic_src,
-            "kernel": "predict_acq_kernel", "kernel_ms": k_ms, "peak_source": peak_src,
+            "kernel": "predict_acq16_kernel (16-warp variant of predict_acq_kernel, the default)", "kernel_ms": k_ms,
+            "peak_source": peak_src,
             "algorithmic_flops_per_candidate": flops_per_candidate(n, d),
             "hbm_model": {"achieved": hbm_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                           "frac": hbm_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "tile_T": 128,
