@@ -27,7 +27,35 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+_NEEDS_REF = ("ExpectedImprovement", "UpperConfidenceBound", "ProbabilityOfImprovement", "ConstantLiar", "GPHedge",
+              "ConstraintModel", "AcquisitionFunction", "bayes_opt", "TS(")
+
+
+def _skip_without_reference(items):
+    """The acquisition-seam classes ARE bayes_opt's classes: without the (vendored) reference package they cannot be
+    imported.  Tests that touch them are skipped with a loud reason instead of erroring; the GP seam / C-ABI tests
+    still run."""
+    try:
+        import bayes_opt  # noqa: F401
+
+        return
+    except ImportError:
+        pass
+    import inspect
+
+    skip = pytest.mark.skip(reason="bayes_opt not importable: run tools/vendor_ref.py where /root/reference exists "
+                                   "(oracle/_ref ships with the repository snapshot)")
+    for item in items:
+        try:
+            src = inspect.getsource(item.function)
+        except (OSError, TypeError, AttributeError):
+            continue
+        if any(tok in src for tok in _NEEDS_REF) or "ref" in getattr(item, "fixturenames", ()):
+            item.add_marker(skip)
+
+
 def pytest_collection_modifyitems(config, items):
+    _skip_without_reference(items)
     try:
         import torch
 

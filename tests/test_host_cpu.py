@@ -317,6 +317,9 @@ def test_bench_reference_arm_contract():
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
     j = json.loads(lines[0])
+    if "unavailable" in j:  # no vendored reference in this checkout: the arm says so in one line and exits 0
+        assert j["impl"] == "reference" and "vendor_ref" in j["unavailable"]
+        pytest.skip("reference package not vendored here")
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
         assert key in j, key
