@@ -1072,9 +1072,9 @@ static int eval_core(const b200bo_acq* spec, const CandSrc& src, int64_t m, doub
     P.acq_out = d_acq_neg;
     P.mu_out = d_mu;
     P.sd_out = d_sd;
-    if ((rc = g0->clamp.reserve(sizeof(unsigned long long)))) return rc;
+    if ((rc = g0->clamp.reserve(2 * sizeof(unsigned long long)))) return rc;
     P.clamp_count = g0->clamp.as<unsigned long long>();
-    if (!sm.resume) CU(cudaMemsetAsync(g0->clamp.p, 0, sizeof(unsigned long long), stream));
+    if (!sm.resume) CU(cudaMemsetAsync(g0->clamp.p, 0, 2 * sizeof(unsigned long long), stream));
     const long long ntiles = (m + PBN - 1) / PBN;
     int grid = (int)(ntiles < g0->sm_count ? ntiles : g0->sm_count);
     if (sm.resume || !sm.finish) grid = g0->sm_count;  // chunked batches keep one list per SM across launches
@@ -1247,6 +1247,14 @@ static int ensure_copy_stream(b200bo_gp* g0) {
     return B200BO_OK;
 }
 
+// sklearn's validate_data rejects NaN / inf in X; the kernels count them while loading the candidates
+static int check_nonfinite(b200bo_gp* g0) {
+    unsigned long long c[2] = {0, 0};
+    CU(cudaMemcpy(c, g0->clamp.p, sizeof(c), cudaMemcpyDeviceToHost));
+    if (c[1] != 0) return set_err(B200BO_ERR_ARG, "Input X contains NaN or infinity.");
+    return B200BO_OK;
+}
+
 static int run_host_chunked(const b200bo_acq* spec, const double* Xc, int64_t m, int k, SelRecord* sel_host) {
     b200bo_gp* g0 = spec->gps[0];
     int rc;
@@ -1276,7 +1284,7 @@ static int run_host_chunked(const b200bo_acq* spec, const double* Xc, int64_t m,
     }
     CU(cudaStreamSynchronize(g0->exec_stream));
     CU(cudaMemcpy(sel_host, g0->sel.p, sizeof(SelRecord) * (k + 1), cudaMemcpyDeviceToHost));
-    return B200BO_OK;
+    return check_nonfinite(g0);
 }
 
 static int run_host(const b200bo_acq* spec, const double* Xc, int64_t m, double* acq_neg, double* mu,
@@ -1322,7 +1330,7 @@ static int run_host(const b200bo_acq* spec, const double* Xc, int64_t m, double*
         CU(cudaMemcpy(&c, g0->clamp.p, sizeof(c), cudaMemcpyDeviceToHost));
         *n_clamped = (int64_t)c;
     }
-    return B200BO_OK;
+    return m > 0 ? check_nonfinite(g0) : B200BO_OK;
 }
 
 extern "C" int b200bo_gp_predict(b200bo_gp* gp, const double* Xc, int64_t m, double* mu, double* sd,
@@ -1704,6 +1712,10 @@ extern "C" int b200bo_multi_gpu_acq_argmin_topk(const b200bo_acq* specs, int n_d
     if (rc) return rc;
     SelRecord sel[B200BO_MAX_TOPK + 1];
     if ((rc = multi_exchange(c, kk, sel))) return rc;
+    for (int g = 0; g < n_dev; ++g) {
+        CU(cudaSetDevice(specs[g].gps[0]->device));
+        if (specs[g].gps[0]->clamp.p && (rc = check_nonfinite(specs[g].gps[0]))) return rc;
+    }
     unpack_records(sel, k, best_val, best_idx, topk_val, topk_idx);
     return B200BO_OK;
 }

@@ -55,12 +55,19 @@ struct PredictParams {
     double* sd_out;    // [m] or nullptr (target GP)
     double* scratch;   // gridDim.x * scratch_stride doubles
     long long scratch_stride;
-    unsigned long long* clamp_count;  // nullable
+    unsigned long long* clamp_count;  // nullable; [0] negative variances clamped to 0, [1] non-finite candidate coordinates
 };
 
 // coordinate j of candidate gi (local index) as the reference's x_tries[gi, j]
+// A non-finite coordinate is counted in clamp_count[1]: the host entry points turn it into the ValueError
+// ("Input X contains NaN or infinity") sklearn's validate_data raises - checked where the data is read anyway instead
+// of a separate pass over the batch on the host (10 ms per 2^20 x 16 batch).
 __device__ __forceinline__ double candidate_coord(const PredictParams& P, long long gi, int j) {
-    if (P.Xc) return P.Xc[gi * P.d + j];
+    if (P.Xc) {
+        const double v = P.Xc[gi * P.d + j];
+        if (!isfinite(v) && P.clamp_count) atomicAdd(P.clamp_count + 1, 1ull);
+        return v;
+    }
     return philox_coord(P.seed, gi + P.index_base, j, P.pbounds[j], P.pbounds[P.d + j]);
 }
 

@@ -113,8 +113,9 @@ class FusedAcquisition:
 
     def _candidates(self, x):
         x = B.c_f64(np.asarray(x, dtype=np.float64).reshape(-1, self.dim))
-        if not np.isfinite(x).all():  # sklearn's predict raises the same way (validate_data)
-            raise ValueError("Input X contains NaN or infinity.")
+        # NaN / inf in x: the kernels count non-finite coordinates while loading them and the C entry point returns
+        # B200BO_ERR_ARG -> ValueError("Input X contains NaN or infinity.") as sklearn's validate_data would - no
+        # separate pass over the batch on the host
         # kernels with a host-side input transform (categorical one-hot): every GP of the call must
         # see the same transformed batch, as in the reference where they share space.kernel_transform
         for g in self._gps:
