@@ -475,6 +475,9 @@ def main():
         c5.pop("_keep")
         extra["c5"] = c5
 
+    if not args.no_extra and args.config == "c3" and rank == 0:
+        extra["other_configs"] = other_config_legs(bo, B, local_rank)
+
     fitleg = None
     if not args.no_extra and args.config == "c3" and rank == 0:
         try:
@@ -487,6 +490,50 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def other_config_legs(bo, B, device):
+    """BASELINE configs[1] (C2: d=8, N=1024, EI, 2^20 candidates) and configs[3] (C4: d=16, N=2048, PoI x 2 constraint
+    GPs, 2^19 candidates) through the public host call (pageable ndarray in, records out), 1 warm-up + 2 timed calls."""
+    from sklearn.gaussian_process.kernels import Matern
+
+    out = {}
+
+    def gp_for(X, y, ls):
+        return bo.B200GaussianProcessRegressor(kernel=Matern(nu=2.5, length_scale=ls), alpha=ALPHA, normalize_y=True,
+                                               optimizer=None, device=device).fit(X, y)
+
+    class Constraint:  # what FusedAcquisition reads of bayes_opt's ConstraintModel
+        pass
+
+    for tag, n, d, m, kind in (("c2_d8_n1024_ei", 1024, 8, 1 << 20, "ei"), ("c4_d16_n2048_poi_2constraints", 2048, 16, 1 << 19, "poi")):
+        rs = np.random.RandomState(0)
+        X = rs.uniform(size=(n, d))
+        y = np.sin(X.sum(1)) + 0.1 * rs.randn(n)
+        gp = gp_for(X, y, 0.7)
+        if kind == "ei":
+            acq = bo.FusedAcquisition(B.ACQ_EI, gp, xi=XI, y_max=float(y.max()))
+            n_gps = 1
+        else:
+            c = np.column_stack([np.cos(X.sum(1)), np.sin(2 * X.sum(1))])
+            con = Constraint()
+            con.model = [gp_for(X, c[:, 0], 0.9), gp_for(X, c[:, 1], 0.5)]
+            con.lb, con.ub = np.array([-np.inf, -0.5]), np.array([0.6, 0.5])
+            ok = np.all((c >= con.lb) & (c <= con.ub), axis=1)
+            acq = bo.FusedAcquisition(B.ACQ_POI, gp, con, xi=XI, y_max=float(y[ok].max()))
+            n_gps = 3
+        xt = np.random.RandomState(1).uniform(size=(m, d))
+        acq.argmin_topk(xt[: m // 8], KSEEDS)
+        ts = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            idx, val, top = acq.argmin_topk(xt, KSEEDS)
+            ts.append(time.perf_counter() - t0)
+        dt = float(np.min(ts))
+        out[tag] = {"candidates": m, "gps_per_candidate": n_gps, "seconds": dt, "value": m / dt, "unit": "candidates/s",
+                    "roofline_frac_fp64": flops_per_candidate(n, d, n_gps) * m / dt / 1e12 / 37.13,
+                    "argmin_index": int(idx), "api": "FusedAcquisition.argmin_topk(host ndarray, 10), wall clock incl. H2D"}
+    return out
 
 
 def fit_and_suggest_legs(bo, cfg, X, y, device):
@@ -618,6 +665,8 @@ def report(args, world, cfg, leg, extra, fitleg, X, y):
             "note": "the candidate set is defined globally (blocks of 2^16 rows regenerated from (buffer, block) seeds), so "
                     "result.argmin_index must be identical for every --gpus N",
         }
+    if "other_configs" in extra:
+        line["other_configs"] = extra["other_configs"]
     if fitleg and "error" in fitleg:
         line["fit"] = fitleg
     elif fitleg:
