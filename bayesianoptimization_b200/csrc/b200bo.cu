@@ -205,6 +205,7 @@ static int init_handle(b200bo_gp* gp) {
     CU(cudaFuncSetAttribute(small_trsv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallTrsvSmemBytes));
     CU(cudaFuncSetAttribute(predict_acq16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDmma));
     CU(cudaFuncSetAttribute(predict_acq16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDmma));
+    CU(cudaFuncSetAttribute(trailing_update64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrailSmemBytes));
     CU(cudaFuncSetAttribute(dgemm128_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemm128SmemBytes));
     CU(cudaFuncSetAttribute(dgemm128_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemm128SmemBytes));
     CU(cudaFuncSetAttribute(dgemm128_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemm128SmemBytes));
@@ -388,6 +389,10 @@ static int potrf_mode() {  // 0 look-ahead (default), 1 serial blocked, 2 legacy
     if (pv && (pv[0] == 's' || pv[0] == 'S')) return 1;
     return 0;
 }
+static int trail_kernel() {  // 1: 64x128 tiles, 2 CTAs/SM (default); 0: the generic 128x128 GEMM (B200BO_TRAIL=gemm)
+    const char* e = getenv("B200BO_TRAIL");
+    return (e && e[0] == 'g') ? 0 : 1;
+}
 static bool gemm_force64() {
     const char* e = getenv("B200BO_GEMM");
     return e && e[0] == '6';
@@ -505,8 +510,14 @@ static int factor_body(b200bo_gp* gp) {
             CU(cudaEventRecord(gp->ev_chain, g_st));  // re-recorded AFTER the wait above was enqueued: now marks step j+1
             if ((rc = gemm<false, true>(below, 64, 64, 1.0, panel, np, 0, Dj, np, 0, 0.0, panel, np, 0, 1, 0, 0, 0, &sb)))
                 return rc;
-            if ((rc = gemm<false, true>(below, below, 64, -1.0, panel, np, 0, panel, np, 0, 1.0,
-                                        L + (size_t)(j0 + 64) * np + j0 + 64, np, 0, 1, 1, 0, 64, &sb, Pside[j & 1])))
+            if (below >= 128 && !gemm_force64() && trail_kernel() == 1) {
+                dim3 grid((below + 127) / 128, below / 64);
+                trailing_update64_kernel<<<grid, 256, kTrailSmemBytes, sb>>>(below, panel, np, L + (size_t)(j0 + 64) * np + j0 + 64,
+                                                                            np, 64, Pside[j & 1]);
+                LAUNCHED();
+                CU(cudaGetLastError());
+            } else if ((rc = gemm<false, true>(below, below, 64, -1.0, panel, np, 0, panel, np, 0, 1.0,
+                                               L + (size_t)(j0 + 64) * np + j0 + 64, np, 0, 1, 1, 0, 64, &sb, Pside[j & 1])))
                 return rc;
             CU(cudaEventRecord(gp->ev_bulk, sb));
         }
@@ -568,7 +579,7 @@ static int run_factor(b200bo_gp* gp) {
                                       (unsigned long long)gp->W.p, (unsigned long long)gp->WT.p, (unsigned long long)gp->T.p,
                                       (unsigned long long)gp->alphav.p, (unsigned long long)gp->y.p, (unsigned long long)gp->v1.p,
                                       (unsigned long long)gp->v2.p, (unsigned long long)gp->info.p, (unsigned long long)gp->pside.p,
-                                      (unsigned long long)(potrf_mode() * 2 + (gemm_force64() ? 1 : 0))};
+                                      (unsigned long long)(potrf_mode() * 4 + trail_kernel() * 2 + (gemm_force64() ? 1 : 0))};
     constexpr int NKEY = sizeof(key) / sizeof(key[0]);
     if (!gp->fgraph_exec || memcmp(key, gp->fgraph_key, sizeof(key)) != 0) {
         if (gp->fgraph_exec) {

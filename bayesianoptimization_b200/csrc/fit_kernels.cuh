@@ -325,6 +325,80 @@ dgemm128_kernel(int M, int N, int K, double alpha, const double* __restrict__ A,
 }
 
 // ---------------------------------------------------------------------------------------
+// Rank-64 trailing update of the blocked Cholesky:  C[M x M] (tiles on/below the diagonal) -= P P^T with P the
+// M x 64 panel (row-major, leading dimension ldp).  A 128x128 GEMM tile spends as long loading its operands and
+// reading / writing C as it spends on its four k-steps of DMMA; here a CTA owns a 64(m) x 128(n) tile, the whole
+// K = 64 of both operands is fetched by ONE batch of cp.async (104 KB of shared memory), and TWO CTAs are resident
+// per SM (<= 128 registers: warp tile 16 x 64), so one CTA's load / C read-modify-write phase runs under the other's
+// DMMA phase.  Same skip / side conventions as dgemm128_kernel.
+// ---------------------------------------------------------------------------------------
+constexpr int TU_STR = 68;  // row stride (doubles) of the mn-major operand tiles: 136 words = 8 (mod 32)
+constexpr int kTrailSmemBytes = (64 + 128) * TU_STR * 8;  // 104448
+__global__ void __launch_bounds__(256, 2)
+trailing_update64_kernel(int M, const double* __restrict__ P, int ldp, double* C, int ldc, int skip,
+                         double* __restrict__ side) {
+    extern __shared__ __align__(16) double tu_smem[];
+    double* As = tu_smem;                 // [64][TU_STR]   rows m0.. of the panel
+    double* Bs = tu_smem + 64 * TU_STR;   // [128][TU_STR]  rows n0.. of the panel
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 128;
+    if (n0 > m0) return;                       // tiles strictly above the diagonal
+    if (m0 + 64 <= skip && n0 + 128 <= skip) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // 64 k = 32 16-byte pieces per row
+    for (int q = tid; q < 64 * 32; q += 256) {
+        const int r = q >> 5, c = (q & 31) * 2;
+        const bool ok = m0 + r < M;
+        cp_async16_zfill(As + r * TU_STR + c, P + (size_t)(ok ? m0 + r : 0) * ldp + c, ok);
+    }
+    for (int q = tid; q < 128 * 32; q += 256) {
+        const int r = q >> 5, c = (q & 31) * 2;
+        const bool ok = n0 + r < M;
+        cp_async16_zfill(Bs + r * TU_STR + c, P + (size_t)(ok ? n0 + r : 0) * ldp + c, ok);
+    }
+    cp_async_commit();
+    const int wm = warp & 3, wn = warp >> 2;
+    const int g = lane >> 2, t4 = lane & 3;
+    double acc[2][8][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    cp_async_wait<0>();
+    __syncthreads();
+#pragma unroll 4
+    for (int k4 = 0; k4 < 16; ++k4) {
+        double a[2], b[8];
+        const int kk = k4 * 4 + t4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) a[i] = As[(wm * 16 + i * 8 + g) * TU_STR + kk];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] = Bs[(wn * 64 + j * 8 + g) * TU_STR + kk];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                             : "d"(a[i]), "d"(b[j]));
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int m = m0 + wm * 16 + i * 8 + g;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = n0 + wn * 64 + j * 8 + 2 * t4;
+            if (n >= M || (m < skip && n < skip)) continue;
+            double2* c = reinterpret_cast<double2*>(C + (size_t)m * ldc + n);
+            const double2 o = *c;
+            const double2 v = make_double2(o.x - acc[i][j][0], o.y - acc[i][j][1]);
+            *c = v;
+            if (side && m >= 64 && m < 128 && n < 64) *reinterpret_cast<double2*>(side + (size_t)(m - 64) * 64 + n) = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Diagonal 64x64 block: in-place Cholesky (lower) + inverse of the factor written to Dinv.
 // Single CTA, 256 threads, phases in potrf_block.cuh (8-column panels: 3 barriers per panel
 // instead of 2 per column, one rsqrt per pivot instead of sqrt + divisions; inverse by recursive

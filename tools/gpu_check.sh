@@ -24,6 +24,8 @@ if [ "$mode" = "bench" ] || [ "$mode" = "all" ]; then
   timeout 1200 python bench.py --steps 5 --warmup 3 > $out/bench.json 2> $out/bench.err; echo "bench exit $?"; cat $out/bench.json; tail -n 5 $out/bench.err
 fi
 if [ "$mode" = "bench" ] || [ "$mode" = "all" ] || [ "$mode" = "fit" ]; then
+  echo "== LML timings (graph / trailing kernel A/B)"
+  python tools/lml_time.py > $out/lml_time.json 2>&1; cat $out/lml_time.json
   echo "== fit / suggest side bench"
   timeout 900 python tools/fit_bench.py > $out/fit_bench.json 2> $out/fit_bench.err; cat $out/fit_bench.json; tail -n 3 $out/fit_bench.err
   B200BO_GEMM=64 B200BO_POTRF=serial timeout 900 python tools/fit_bench.py > $out/fit_bench_gemm64.json 2> $out/fit_bench_gemm64.err; cat $out/fit_bench_gemm64.json

@@ -8,8 +8,9 @@ out = {}
 for n, d in [(1024, 8), (4096, 16)]:
     rs = np.random.RandomState(0)
     X = rs.uniform(size=(n, d)); y = np.sin(X.sum(1)) + 0.1 * rs.randn(n)
-    for mode in ("graph", "direct", "direct_serial_gemm64"):
-        os.environ["B200BO_GRAPH"] = "1" if mode == "graph" else "0"
+    for mode in ("graph", "graph_trail_gemm128", "direct", "direct_serial_gemm64"):
+        os.environ["B200BO_GRAPH"] = "1" if mode.startswith("graph") else "0"
+        os.environ["B200BO_TRAIL"] = "gemm" if mode == "graph_trail_gemm128" else "tile64"
         if mode == "direct_serial_gemm64":
             os.environ["B200BO_POTRF"], os.environ["B200BO_GEMM"] = "serial", "64"
         else:
