@@ -400,6 +400,11 @@ def main():
                "launches": int(launches), "clocks": clocks, "result": {"argmin_index": res[0], "argmin_value": res[1],
                                                                       "top_indices": res[2]},
                "m_local": int(m_local), "m_step": int(m_step), "fit_s": fit_s}
+        if world > 1:  # every rank's own mean kernel time (the step time is the max over ranks: GPUs of a box differ by a few %)
+            t = torch.tensor([out["kernel_ms"]], dtype=torch.float64, device=dev)
+            allk = torch.zeros(world, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allk, t)
+            out["kernel_ms_per_rank"] = [round(float(v), 2) for v in allk.cpu()]
         if world > 1:  # the exchange alone, device-timed
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
@@ -627,6 +632,7 @@ def report(args, world, cfg, leg, extra, fitleg, X, y):
     })
     if "exchange_ms" in leg:
         line["exchange_ms"] = leg["exchange_ms"]
+        line["kernel_ms_per_rank"] = leg.get("kernel_ms_per_rank")
     if "fp32" in extra:
         f = extra["fp32"]
         tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0
@@ -660,7 +666,7 @@ def report(args, world, cfg, leg, extra, fitleg, X, y):
         line["c5_strong"] = {
             "what": c5cfg["label"], "scaling": "strong", "value": c["value"], "unit": "candidates/s",
             "ms_per_step": c["ms_per_step"], "kernel_ms": c["kernel_ms"], "candidates_per_rank": c["m_local"],
-            "exchange_ms": c.get("exchange_ms"), "result": c["result"],
+            "exchange_ms": c.get("exchange_ms"), "kernel_ms_per_rank": c.get("kernel_ms_per_rank"), "result": c["result"],
             "roofline_frac_fp64": fl / (c["kernel_ms"] * 1e-3) / 1e12 / fp64_peak,
             "note": "the candidate set is defined globally (blocks of 2^16 rows regenerated from (buffer, block) seeds), so "
                     "result.argmin_index must be identical for every --gpus N",
