@@ -510,7 +510,7 @@ static int factor_body(b200bo_gp* gp) {
             CU(cudaEventRecord(gp->ev_chain, g_st));  // re-recorded AFTER the wait above was enqueued: now marks step j+1
             if ((rc = gemm<false, true>(below, 64, 64, 1.0, panel, np, 0, Dj, np, 0, 0.0, panel, np, 0, 1, 0, 0, 0, &sb)))
                 return rc;
-            if (below >= 128 && !gemm_force64() && trail_kernel() == 1) {
+            if (below >= 1024 && !gemm_force64() && trail_kernel() == 1) {  // large updates only: measured no gain below
                 dim3 grid((below + 127) / 128, below / 64);
                 trailing_update64_kernel<<<grid, 256, kTrailSmemBytes, sb>>>(below, panel, np, L + (size_t)(j0 + 64) * np + j0 + 64,
                                                                             np, 64, Pside[j & 1]);
@@ -573,8 +573,10 @@ static int run_factor(b200bo_gp* gp) {
     int rc;
     if ((rc = ensure_bulk_stream(gp))) return rc;
     if ((rc = gp->pside.reserve(sizeof(double) * 2 * 64 * 64))) return rc;
+    // graphs pay off where the launch-by-launch host cost matters (measured: N=4096 5.70 vs 5.92 ms; N=1024 no gain) and
+    // cost a capture + instantiation per handle and size: used from np >= 2048 (B200BO_GRAPH=0 never, =1 always)
     const char* ge = getenv("B200BO_GRAPH");
-    if (ge && ge[0] == '0') return factor_body(gp);
+    if ((ge && ge[0] == '0') || (!(ge && ge[0] == '1') && gp->np < 2048)) return factor_body(gp);
     const unsigned long long key[] = {(unsigned long long)gp->np, (unsigned long long)gp->K.p, (unsigned long long)gp->L.p,
                                       (unsigned long long)gp->W.p, (unsigned long long)gp->WT.p, (unsigned long long)gp->T.p,
                                       (unsigned long long)gp->alphav.p, (unsigned long long)gp->y.p, (unsigned long long)gp->v1.p,
