@@ -1122,7 +1122,7 @@ static int eval_core(const b200bo_acq* spec, const CandSrc& src, int64_t m, doub
             const int npass = (int)((left + SMC - 1) / SMC < SMAXP ? (left + SMC - 1) / SMC : SMAXP);
             for (int g = 0; g < spec->n_gps; ++g) {
                 small_kstar_kernel<<<dim3(spec->gps[g]->np / 128, npass), 256, 0, stream>>>(S, g);
-                small_trsv_kernel<<<spec->gps[g]->s_nunits, 256, kSmallTrsvSmemBytes, stream>>>(S, g, npass);
+                small_trsv_kernel<<<dim3(spec->gps[g]->s_nunits, (npass + STPG - 1) / STPG), 256, kSmallTrsvSmemBytes, stream>>>(S, g, npass);
                 small_reduce_kernel<<<dim3(spec->gps[g]->np / SROWS, npass), 256, 0, stream>>>(S, g);
                 LAUNCHED();
                 LAUNCHED();

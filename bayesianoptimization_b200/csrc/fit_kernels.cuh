@@ -431,20 +431,21 @@ potrf_diag_kernel(double* A, int ld, int j0, double* Dinv, int ldd, int* info, c
     }
     __syncthreads();
     if (Pprev) {
-        // 4x4 register tiles: thread (ti, tj) owns rows 4ti..4ti+3, columns 4tj..4tj+3 (8 shared loads per 16 FMAs)
+        // 4x4 register tiles with STRIDED ownership: thread (ti, tj) owns rows ti + 16 i and columns tj + 16 j.  With
+        // the row stride of 65 doubles the 16 tj-lanes of a half-warp then read 16 different even banks (contiguous
+        // 4-column ownership put lanes tj and tj+4 on the same banks: a 4-way conflict on every operand load).
         const int tj = tid & 15, ti = tid >> 4;
         double acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-        const int kmax = 4 * tj + 3;  // Dprev is lower triangular: D[c][k] = 0 for k > c
-        for (int k = 0; k <= kmax; ++k) {
+        for (int k = 0; k < kB; ++k) {  // Dprev was loaded with zeros above its diagonal
             double p[4], dd[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) p[i] = V[(4 * ti + i) * kLd + k];
+            for (int i = 0; i < 4; ++i) p[i] = V[(ti + 16 * i) * kLd + k];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dd[j] = T[(4 * tj + j) * kLd + k];  // zero above the diagonal (loaded so)
+            for (int j = 0; j < 4; ++j) dd[j] = T[(tj + 16 * j) * kLd + k];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -454,30 +455,28 @@ potrf_diag_kernel(double* A, int ld, int j0, double* Dinv, int ldd, int* info, c
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) V[(4 * ti + i) * kLd + 4 * tj + j] = acc[i][j];  // X over P
+            for (int j = 0; j < 4; ++j) V[(ti + 16 * i) * kLd + tj + 16 * j] = acc[i][j];  // X over P
         __syncthreads();
-        if (tj <= ti) {  // lower tiles of S -= X X^T
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        for (int k = 0; k < kB; ++k) {
+            double xr[4], xc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xr[i] = V[(ti + 16 * i) * kLd + k];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xc[j] = V[(tj + 16 * j) * kLd + k];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-            for (int k = 0; k < kB; ++k) {
-                double xr[4], xc[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) xr[i] = V[(4 * ti + i) * kLd + k];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) xc[j] = V[(4 * tj + j) * kLd + k];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = fma(xr[i], xc[j], acc[i][j]);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (4 * tj + j <= 4 * ti + i) S[(4 * ti + i) * kLd + 4 * tj + j] -= acc[i][j];
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(xr[i], xc[j], acc[i][j]);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (tj + 16 * j <= ti + 16 * i) S[(ti + 16 * i) * kLd + tj + 16 * j] -= acc[i][j];  // lower part of S -= X X^T
         __syncthreads();
         for (int idx = tid; idx < kB * kB; idx += kThreads) V[(idx >> 6) * kLd + (idx & 63)] = 0.0;
         __syncthreads();

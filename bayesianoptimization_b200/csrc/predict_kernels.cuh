@@ -1166,25 +1166,29 @@ small_kstar_kernel(const SmallParams S, int g) {
     }
 }
 
-// Partial V for one work unit (64 rows x <= 512 k) and ALL passes of the launch group: the W tile is staged once
-// per k sub-tile and used for every pass (the passes used to be separate CTAs that each re-read L^-1).
-constexpr int kSmallTrsvSmemBytes = (SROWS * SWSTR + SMAXP * SKT * SMC) * 8;  // 82944
-__global__ void __launch_bounds__(256)
+// Partial V for one work unit (64 rows x <= 512 k) and a GROUP of up to STPG passes (blockIdx.y = group): the W tile
+// is staged once per k sub-tile and used for every pass of the group.  (One CTA per pass re-read L^-1 six times per
+// round; all eight passes in one CTA needed 178 registers and 83 KB -> one CTA per SM, half the throughput.  Groups
+// of four: ~100 registers, 49 KB -> two to three resident CTAs per SM.)
+constexpr int STPG = 4;
+constexpr int kSmallTrsvSmemBytes = (SROWS * SWSTR + STPG * SKT * SMC) * 8;  // 50176
+__global__ void __launch_bounds__(256, 2)
 small_trsv_kernel(const SmallParams S, int g, int npass) {
     const GpDev& G = S.P.gp[g];
     const SmallGp& Q = S.sg[g];
     extern __shared__ __align__(16) double strsv_smem[];
     double* Wt = strsv_smem;                  // [SROWS][SWSTR]
-    double* Kt = strsv_smem + SROWS * SWSTR;  // [npass][SKT][SMC]
+    double* Kt = strsv_smem + SROWS * SWSTR;  // [STPG][SKT][SMC]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int p0 = blockIdx.y * STPG, pn = min(STPG, npass - p0);
     const int2 u = Q.unit_tab[blockIdx.x];
     const int r0 = u.x * SROWS;
     const int kbeg = u.y * SKCH;
     const int kend = min(kbeg + SKCH, r0 + SROWS);
     const int np = G.np;
-    double acc[SMAXP][8];
+    double acc[STPG][8];
 #pragma unroll
-    for (int p = 0; p < SMAXP; ++p)
+    for (int p = 0; p < STPG; ++p)
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[p][q] = 0.0;
     for (int k0 = kbeg; k0 < kend; k0 += SKT) {
@@ -1192,8 +1196,8 @@ small_trsv_kernel(const SmallParams S, int g, int npass) {
             const int r = idx / SKT, kk = idx % SKT;
             Wt[r * SWSTR + kk] = Q.W[(size_t)(r0 + r) * np + k0 + kk];
         }
-        for (int p = 0; p < npass; ++p) {
-            const double* ksm = Q.ksm + (size_t)p * np * SMC + (size_t)k0 * SMC;
+        for (int p = 0; p < pn; ++p) {
+            const double* ksm = Q.ksm + (size_t)(p0 + p) * np * SMC + (size_t)k0 * SMC;
             for (int idx = tid; idx < SKT * SMC; idx += 256) Kt[p * SKT * SMC + idx] = ksm[idx];
         }
         __syncthreads();
@@ -1203,8 +1207,8 @@ small_trsv_kernel(const SmallParams S, int g, int npass) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) w[q] = *reinterpret_cast<const double2*>(&Wt[(warp * 8 + q) * SWSTR + kk]);
 #pragma unroll
-            for (int p = 0; p < SMAXP; ++p) {
-                if (p < npass) {
+            for (int p = 0; p < STPG; ++p) {
+                if (p < pn) {
                     const double k0v = Kt[p * SKT * SMC + kk * SMC + lane], k1v = Kt[p * SKT * SMC + (kk + 1) * SMC + lane];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
@@ -1217,9 +1221,9 @@ small_trsv_kernel(const SmallParams S, int g, int npass) {
         __syncthreads();
     }
 #pragma unroll
-    for (int p = 0; p < SMAXP; ++p) {
-        if (p < npass) {
-            double* out = Q.partial + ((size_t)p * S.nunits[g] + blockIdx.x) * SROWS * SMC;
+    for (int p = 0; p < STPG; ++p) {
+        if (p < pn) {
+            double* out = Q.partial + ((size_t)(p0 + p) * S.nunits[g] + blockIdx.x) * SROWS * SMC;
 #pragma unroll
             for (int q = 0; q < 8; ++q) out[(warp * 8 + q) * SMC + lane] = acc[p][q];
         }
