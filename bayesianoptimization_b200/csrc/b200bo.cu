@@ -202,6 +202,7 @@ static int init_handle(b200bo_gp* gp) {
     CU(cudaFuncSetAttribute(predict_acq_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             kPredictSmemBytesTc2));
     CU(cudaFuncSetAttribute(predict_acq_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesTc3));
+    CU(cudaFuncSetAttribute(predict_acq_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesTc4));
     CU(cudaFuncSetAttribute(small_trsv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallTrsvSmemBytes));
     CU(cudaFuncSetAttribute(predict_acq16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDmma));
     CU(cudaFuncSetAttribute(predict_acq16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPredictSmemBytesDmma));
@@ -1154,15 +1155,18 @@ static int eval_core(const b200bo_acq* spec, const CandSrc& src, int64_t m, doub
             }
             CU(cudaEventRecord(g0->ev0, stream));  // exclude the one-off tiling from the kernel time
             const char* tv = getenv("B200BO_TC_VARIANT");  // "1": non-overlapped version, "2"/"3": see kDefaultTcVariant
-            const int variant = (tv && tv[0] >= '1' && tv[0] <= '3') ? tv[0] - '0' : kDefaultTcVariant;
-            if (dreg && variant == 3) {
+            const int variant = (tv && tv[0] >= '1' && tv[0] <= '4') ? tv[0] - '0' : kDefaultTcVariant;
+            if (dreg && (variant == 3 || variant == 4)) {
                 // N = 256 per MMA: candidate tiles of 256, two K* image buffers of np x 2 KiB per CTA
                 const long long nt3 = (m + T3N - 1) / T3N;
                 if (!(sm.resume || !sm.finish)) grid = (int)(nt3 < g0->sm_count ? nt3 : g0->sm_count);
                 P.scratch_stride = (long long)np_max * 512;
                 if ((rc = g0->pscratch.reserve(sizeof(double) * (size_t)P.scratch_stride * g0->sm_count))) return rc;
                 P.scratch = g0->pscratch.as<double>();
-                predict_acq_tc3_kernel<<<grid, TC2_NT, kPredictSmemBytesTc3, stream>>>(P);
+                if (variant == 4)
+                    predict_acq_tc4_kernel<<<grid, TC2_NT, kPredictSmemBytesTc4, stream>>>(P);
+                else
+                    predict_acq_tc3_kernel<<<grid, TC2_NT, kPredictSmemBytesTc3, stream>>>(P);
             } else if (dreg && variant != 1) {
                 // overlapped version: two K* image buffers per CTA
                 P.scratch_stride *= 2;

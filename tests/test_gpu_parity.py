@@ -792,7 +792,7 @@ def test_mixed_int_space_round_transform_and_de_branch(bo, golden, TS):
     assert_allclose(sug, g["suggestion"], rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("variant", ["overlapped", "sequential", "n256"])
+@pytest.mark.parametrize("variant", ["overlapped", "sequential", "n256", "n256pair"])
 @pytest.mark.parametrize("n,d,m", [(300, 4, 1000), (1024, 8, 20_000), (4096, 16, 40_000), (500, 20, 3000)])
 def test_fp32_mode_tcgen05_vs_oracle(bo, O, n, d, m, variant, monkeypatch):
     """fp32 mode (precision="fp32"): the N^2 term on tcgen05 tensor cores (3xTF32, fp32 accumulate
@@ -809,7 +809,7 @@ def test_fp32_mode_tcgen05_vs_oracle(bo, O, n, d, m, variant, monkeypatch):
     a.y_max = float(y.max())
     f = a._get_acq(gp=gp)
     monkeypatch.setenv("B200BO_SMALL_PATH", "0")
-    monkeypatch.setenv("B200BO_TC_VARIANT", {"sequential": "1", "overlapped": "2", "n256": "3"}[variant])
+    monkeypatch.setenv("B200BO_TC_VARIANT", {"sequential": "1", "overlapped": "2", "n256": "3", "n256pair": "4"}[variant])
     mu, sd = gp.predict(xt, return_std=True)
     ys = f(xt)
     idx, val, top = f.argmin_topk(xt, 10)

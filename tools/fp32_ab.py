@@ -1,5 +1,5 @@
 """A/B of the fp32-mode kernels at C3 (d=16, N=4096, EI, 2^20 candidates resident in HBM): variant 2 (row-block
-pairs x 128 candidates) vs variant 3 (N = 256 per MMA), interleaved so both see the same clocks / power state."""
+pairs x 128 candidates) vs variant 3 (N = 256 per MMA) vs variant 4 (N = 256, row-block pairs), interleaved so both see the same clocks / power state."""
 import ctypes as C, json, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -17,9 +17,9 @@ dev = torch.device("cuda", 0)
 bufs = [torch.from_numpy(np.random.RandomState(100 + b).uniform(size=(m, d))).to(dev) for b in range(3)]
 sel = torch.zeros((11, 2), dtype=torch.int64, device=dev)
 L = B.lib(); stream = torch.cuda.current_stream()
-out = {"2": [], "3": []}; res = {}
+out = {"2": [], "3": [], "4": []}; res = {}
 for rep in range(6):
-    for v in ("2", "3"):
+    for v in ("2", "3", "4"):
         os.environ["B200BO_TC_VARIANT"] = v
         B.check(L.b200bo_acq_eval_dev(C.byref(acq.spec), bufs[rep % 3].data_ptr(), m, None, None, None, 10, sel.data_ptr(), 0, stream.cuda_stream))
         ms = C.c_float(); B.check(L.b200bo_last_kernel_ms(C.byref(ms)))
@@ -28,4 +28,4 @@ for rep in range(6):
         res[v] = sel.cpu().numpy()[:, 1].tolist()
 print(json.dumps({"kernel_ms": {k: float(np.mean(v)) for k, v in out.items()}, "all": out,
                   "cand_per_s": {k: m / (np.mean(v) * 1e-3) for k, v in out.items()},
-                  "same_selection": res["2"] == res["3"], "sel2": res["2"][:4], "sel3": res["3"][:4]}))
+                  "same_selection": res["2"] == res["3"] == res["4"], "sel2": res["2"][:4], "sel4": res["4"][:4]}))
