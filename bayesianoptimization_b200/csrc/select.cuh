@@ -92,8 +92,10 @@ __device__ __forceinline__ void runsel_update(SelShared& S, int k, int t, double
         S.sidx[pos] = gi;
     }
     named_bar_sync_sel(BAR, 128);
-    if (t == 0 && S.nstage > 0) {
-        const int ns = S.nstage;
+    if (t == 0) {
+        // only thread 0 reads the counter in this interval (it also resets it below): no other thread's speculative
+        // load of it may race with that write
+        const int ns = *reinterpret_cast<volatile int*>(&S.nstage);
         for (int s = 0; s < ns; ++s) {
             const unsigned long long nk = S.skey[s];
             const long long ni = S.sidx[s];
@@ -107,7 +109,7 @@ __device__ __forceinline__ void runsel_update(SelShared& S, int k, int t, double
             S.list.key[p] = nk;
             S.list.idx[p] = ni;
         }
-        S.nstage = 0;
+        if (ns > 0) S.nstage = 0;
     }
     named_bar_sync_sel(BAR, 128);
 }
