@@ -24,7 +24,7 @@
 
 using namespace b200bo;
 
-constexpr int kDefaultTcVariant = 3;  // fp32 mode: 3 = N = 256 per MMA (predict_tc3.cuh; measured 121.9 vs 128.4 ms, same box), 2 = row-block pairs x 128
+constexpr int kDefaultTcVariant = 4;  // fp32 mode: 4 = N = 256 per MMA + row-block pairs (measured 115.7 ms; 3 = un-paired 124.7; 2 = 128-wide pairs 120.6, same box)
 constexpr int kDefaultPredictWarps = 16;  // measured A/B: 550.1 ms vs 561.7 ms per 2^20 candidates at C3
 
 // ---------------------------------------------------------------------------------------

@@ -637,12 +637,12 @@ def report(args, world, cfg, leg, extra, fitleg, X, y):
         f = extra["fp32"]
         tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0
         executed = 3.0 * n * n * f["m_local"] / (f["kernel_ms"] * 1e-3) / 1e12  # 3 TF32 products per multiply-add
-        t32, t32_src = ncu_traffic("predict_acq_tc3_kernel")
+        t32, t32_src = ncu_traffic("predict_acq_tc4_kernel")
         line["fp32_mode"] = {
             "what": "same workload, N^2 term as 3xTF32 on tcgen05 (fp32 accumulate in TMEM); K*, mean, epilogue fp64",
             "value": f["value"], "unit": "candidates/s", "e2e": f.get("e2e"), "kernel_ms": f["kernel_ms"],
             "tolerance": "1e-3 rel on the predictive variance (+1e-4 s_y^2 atol), tests/test_gpu_parity.py",
-            "kernel": "predict_acq_tc3_kernel (N = 256 per tcgen05.mma; tc2 = row-block pairs, B200BO_TC_VARIANT=2)", "clocks": f["clocks"],
+            "kernel": "predict_acq_tc4_kernel (N = 256 per tcgen05.mma, row-block pairs; B200BO_TC_VARIANT=2|3 select the earlier variants)", "clocks": f["clocks"],
             "roofline": {"bound": "tensor", "achieved": executed, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": executed / tf32_peak, "traffic": t32, "traffic_source": t32_src,
                          "note": "executed TF32 tensor flops (3 products per useful multiply-add); dense TF32 peak "

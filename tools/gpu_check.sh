@@ -45,9 +45,9 @@ if [ "$mode" = "prof" ]; then
      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > $out/ncu_full8.log 2>&1
   echo "ncu full exit $?"; summarise $out/prof_predict8
   echo "== ncu full (fp32-mode kernel)"
-  B200BO_PREDICT_IMPL=tf32 timeout 900 ncu --set full --clock-control none -k regex:predict_acq_tc3 -s 3 -c 1 -o $out/prof_predict_tc3 -f \
-     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > $out/ncu_full_tc3.log 2>&1
-  echo "ncu tc3 exit $?"; summarise $out/prof_predict_tc3
+  B200BO_PREDICT_IMPL=tf32 timeout 900 ncu --set full --clock-control none -k regex:predict_acq_tc4 -s 3 -c 1 -o $out/prof_predict_tc4 -f \
+     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > $out/ncu_full_tc4.log 2>&1
+  echo "ncu tc4 exit $?"; summarise $out/prof_predict_tc4
   echo "== launch list + full captures of the fit-side kernels (one fit + one LML+gradient evaluation, N=4096; graph off)"
   B200BO_GRAPH=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches_lml.csv python tools/lml_once.py > $out/lml_once.log 2>&1
   gzip -f $out/launches_lml.csv
