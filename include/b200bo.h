@@ -188,7 +188,11 @@ int b200bo_acq_eval(const b200bo_acq* spec, const double* Xc, int64_t m, double*
  * (R/bayes_opt/acquisition.py:311-317): evaluates the closure on Xc and returns
  *   best_idx/best_val = np.argmin semantics (first NaN wins; ties -> lowest index),
  *   topk_idx/topk_val = the k smallest in (value, index) order, NaN last (np.argsort order).
- * acq_neg (nullable) additionally receives all m values. */
+ * acq_neg (nullable) additionally receives all m values.  The values are NOT materialised otherwise: every CTA of the
+ * fused kernel keeps its k best (key, index) pairs and a small kernel merges the lists.  Batches of >= 2 chunks
+ * (8 x 128 x #SM rows) are uploaded chunk by chunk on a copy stream behind the kernel.  A NaN / inf candidate coordinate
+ * is detected where the kernels read it and reported as B200BO_ERR_ARG ("Input X contains NaN or infinity.", what
+ * sklearn's validate_data raises on the reference path); the same holds for b200bo_acq_eval / b200bo_gp_predict. */
 int b200bo_acq_argmin_topk(const b200bo_acq* spec, const double* Xc, int64_t m, int k,
                            double* best_val, int64_t* best_idx, double* topk_val,
                            int64_t* topk_idx, double* acq_neg);
