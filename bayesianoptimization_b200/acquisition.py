@@ -163,3 +163,11 @@ class GPHedge(_ref.GPHedge):
 
     def __init__(self, base_acquisitions, *args, **kwargs):
         super().__init__([accelerate(a) for a in base_acquisitions], *args, **kwargs)
+
+
+# isinstance(x, b200.AcquisitionFunction) holds for every acquisition of this module, as
+# isinstance(x, bayes_opt.acquisition.AcquisitionFunction) does in the reference (abc virtual subclasses:
+# the concrete classes keep the reference's MRO).
+for _cls in (UpperConfidenceBound, ProbabilityOfImprovement, ExpectedImprovement, ConstantLiar, GPHedge):
+    AcquisitionFunction.register(_cls)
+del _cls

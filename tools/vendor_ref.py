@@ -28,6 +28,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get("B200BO_REFERENCE", "/root/reference")
 DST = os.path.join(ROOT, "oracle", "_ref")
+# the reference's test modules that exercise the hot path and its callers
+REF_TESTS = ("test_acquisition.py", "test_constraint.py", "test_bayesian_optimization.py", "test_target_space.py",
+             "test_seq_domain_red.py")
 
 
 def reference_version() -> str:
@@ -51,7 +54,8 @@ def vendor(force: bool = False) -> str | None:
         return DST if os.path.isdir(os.path.join(DST, "bayes_opt")) else None
     stamp = os.path.join(DST, ".vendored")
     ver = reference_version()
-    if not force and os.path.exists(stamp) and open(stamp).read().strip() == ver:
+    if (not force and os.path.exists(stamp) and open(stamp).read().strip() == ver
+            and os.path.isdir(os.path.join(DST, "ref_tests"))):
         return DST
     if os.path.isdir(DST):
         _make_writable(DST)
@@ -61,6 +65,12 @@ def vendor(force: bool = False) -> str | None:
     shutil.copytree(os.path.join(ROOT, "oracle", "shims", "colorama"), os.path.join(DST, "colorama"),
                     ignore=shutil.ignore_patterns("__pycache__"))
     _make_writable(DST)  # /root/reference is read-only and copytree keeps the modes
+    # the reference's own tests for the path: run on the GPU box against the drop-in (tests/test_gpu_reference_suite.py)
+    tdst = os.path.join(DST, "ref_tests")
+    os.makedirs(tdst)
+    for name in REF_TESTS:
+        shutil.copy(os.path.join(REF, "tests", name), os.path.join(tdst, name))
+    _make_writable(DST)
     info = os.path.join(DST, f"bayesian_optimization-{ver}.dist-info")
     os.makedirs(info)
     with open(os.path.join(info, "METADATA"), "w") as f:
