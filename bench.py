@@ -482,6 +482,10 @@ def main():
 
     if not args.no_extra and args.config == "c3" and rank == 0:
         extra["other_configs"] = other_config_legs(bo, B, local_rank)
+        try:
+            extra["other_configs"]["c1_readme_n25_ucb_live"] = c1_live_leg(bo, local_rank)
+        except ImportError as e:  # bayes_opt not importable
+            extra["other_configs"]["c1_readme_n25_ucb_live"] = {"error": str(e)}
 
     fitleg = None
     if not args.no_extra and args.config == "c3" and rank == 0:
@@ -539,6 +543,42 @@ def other_config_legs(bo, B, device):
                     "roofline_frac_fp64": flops_per_candidate(n, d, n_gps) * m / dt / 1e12 / 37.13,
                     "argmin_index": int(idx), "api": "FusedAcquisition.argmin_topk(host ndarray, 10), wall clock incl. H2D"}
     return out
+
+
+def c1_live_leg(bo, device):
+    """BASELINE configs[0]: the README's 2-D black_box_function, Matern nu=2.5, UCB, maximize(init_points=5, n_iter=20)
+    (N_train reaches 25) through the reference's own BayesianOptimization driver - stock (sklearn / SciPy on the host
+    cores) and with enable() (every fit / suggest on the device).  Wall seconds of the whole loop; the enabled loop is
+    run twice and the second run reported (the first pays the one-off allocations)."""
+    import warnings
+
+    from bayes_opt import BayesianOptimization
+
+    def black_box(x, y):
+        return -(x**2) - (y - 1) ** 2 + 1
+
+    def run(enabled):
+        opt = BayesianOptimization(f=black_box, pbounds={"x": (2, 4), "y": (-3, 3)}, random_state=1, verbose=0)
+        if enabled:
+            bo.enable(opt, device=device)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t0 = time.perf_counter()
+            opt.maximize(init_points=5, n_iter=20)
+            dt = time.perf_counter() - t0
+        return dt, opt
+
+    run(True)
+    t_dev, o_dev = run(True)
+    t_ref, o_ref = run(False)
+    p_dev, p_ref = o_dev.space.params, o_ref.space.params
+    return {"what": "maximize(init_points=5, n_iter=20) of the README example through bayes_opt.BayesianOptimization, wall "
+                    "seconds: enable()d (device) vs stock (host cores)",
+            "seconds": t_dev, "seconds_reference_cpu": t_ref, "iterations": 20,
+            "max_target": float(o_dev.max["target"]), "max_target_reference": float(o_ref.max["target"]),
+            "max_abs_diff_of_probed_points": float(np.max(np.abs(p_dev - p_ref))) if p_dev.shape == p_ref.shape else None,
+            "same_rng_state_after": bool(all(np.array_equal(a, b) for a, b in zip(
+                o_dev._random_state.get_state()[1:3], o_ref._random_state.get_state()[1:3])))}
 
 
 def fit_and_suggest_legs(bo, cfg, X, y, device):
