@@ -484,15 +484,15 @@ def main():
         extra["other_configs"] = other_config_legs(bo, B, local_rank)
         try:
             extra["other_configs"]["c1_readme_n25_ucb_live"] = c1_live_leg(bo, local_rank)
-        except ImportError as e:  # bayes_opt not importable
-            extra["other_configs"]["c1_readme_n25_ucb_live"] = {"error": str(e)}
+        except Exception as e:  # a secondary leg never takes the headline line down (e.g. bayes_opt not importable)
+            extra["other_configs"]["c1_readme_n25_ucb_live"] = {"error": repr(e)}
 
     fitleg = None
     if not args.no_extra and args.config == "c3" and rank == 0:
         try:
             fitleg = fit_and_suggest_legs(bo, cfg, X, y, local_rank)
-        except ImportError as e:  # bayes_opt not importable: the acquisition-seam legs cannot run
-            fitleg = {"error": str(e)}
+        except Exception as e:  # e.g. bayes_opt not importable: the acquisition-seam legs cannot run
+            fitleg = {"error": repr(e)}
 
     if rank == 0:
         emit(report(args, world, cfg, main_leg, extra, fitleg, X, y))
