@@ -30,7 +30,7 @@ REF = os.environ.get("B200BO_REFERENCE", "/root/reference")
 DST = os.path.join(ROOT, "oracle", "_ref")
 # the reference's test modules that exercise the hot path and its callers
 REF_TESTS = ("test_acquisition.py", "test_constraint.py", "test_bayesian_optimization.py", "test_target_space.py",
-             "test_seq_domain_red.py")
+             "test_seq_domain_red.py", "test_parameter.py", "test_util.py", "test_logger.py")
 
 
 def reference_version() -> str:
@@ -55,7 +55,7 @@ def vendor(force: bool = False) -> str | None:
     stamp = os.path.join(DST, ".vendored")
     ver = reference_version()
     if (not force and os.path.exists(stamp) and open(stamp).read().strip() == ver
-            and os.path.isdir(os.path.join(DST, "ref_tests"))):
+            and all(os.path.exists(os.path.join(DST, "ref_tests", t)) for t in REF_TESTS)):
         return DST
     if os.path.isdir(DST):
         _make_writable(DST)
