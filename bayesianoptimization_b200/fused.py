@@ -123,7 +123,9 @@ class FusedAcquisition:
         modes = [g.__dict__.get("_b200_xform", ("device", None)) for g in self._gps]
         host = [a for m, a in modes if m == "host"]
         if host:
-            if len(host) != len(modes) or any(h is not host[0] for h in host):
+            # `==`, not `is`: the reference hands every GP `space.kernel_transform`, a bound method - each attribute
+            # access makes a new method object, equal iff same function of the same space
+            if len(host) != len(modes) or any(h != host[0] for h in host):
                 raise NotImplementedError("GPs of one acquisition call use different host-side input transforms")
             x = self._gps[0]._device_candidates(x)
         return x
