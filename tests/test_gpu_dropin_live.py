@@ -206,6 +206,38 @@ def test_int_and_categorical_parameters_live(ref, bo):
             b._random_state.set_state(a._random_state.get_state())  # DE consumes the stream per generation
 
 
+def test_categorical_parameter_with_constraint_live(ref, bo):
+    """Constraint GP + categorical parameter: target and constraint GPs both carry the space's one-hot kernel transform
+    (two bound-method objects of the same TargetSpace, R/bayes_opt/target_space.py:105-111) and must share ONE transformed
+    batch per device call.  (Found by the reference's own test_parameter.py on the drop-in; this pins it stepwise.)"""
+    from scipy.optimize import NonlinearConstraint
+
+    score = {"a": 0.0, "b": 1.0, "c": -0.5}
+
+    def f(x, k, c):
+        return -((x - 2.0) ** 2) - 0.3 * (k - 3) ** 2 + score[c]
+
+    def g(x, k, c):
+        return x + 0.5 * k - score[c]
+
+    pb = {"x": (0.0, 5.0), "k": (0, 6, int), "c": ["a", "b", "c"]}
+    a, b = _pair(ref, bo, 13, f=f, pbounds=pb, constraint=NonlinearConstraint(g, 0.5, 4.5))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for o in (a, b):
+            o.maximize(init_points=8, n_iter=0)
+        for _ in range(3):
+            sa, sb = a.suggest(), b.suggest()
+            xa, xb = _as_array(a, sa), _as_array(b, sb)
+            va, vb = _ref_closure_values(a, xa, xb)
+            same = sa["k"] == sb["k"] and sa["c"] == sb["c"] and abs(sa["x"] - sb["x"]) < 2e-2
+            assert same or vb <= va + 1e-3 * max(abs(va), 1e-9), (sa, sb, va, vb)
+            assert isinstance(sb["c"], str) and float(sb["k"]).is_integer()
+            for o in (a, b):
+                o.register(params=sa, target=f(**sa), constraint_value=g(**sa))
+            b._random_state.set_state(a._random_state.get_state())  # DE consumes the stream per generation
+
+
 def test_maximize_runs_end_to_end_on_device(ref, bo):
     """optimizer.maximize() (bayesian_optimization.py:348-391) on an enabled optimizer: runs, improves,
     every launch is the package's own."""
