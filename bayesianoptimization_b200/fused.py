@@ -154,7 +154,8 @@ class FusedAcquisition:
             off = None
             if shard_offsets is not None:
                 off = np.ascontiguousarray(shard_offsets, dtype=np.int64)
-                assert off.shape == (len(self.devices) + 1,) and off[0] == 0 and off[-1] == m
+                if off.shape != (len(self.devices) + 1,) or off[0] != 0 or off[-1] != m or np.any(np.diff(off) < 0):
+                    raise ValueError("shard_offsets must be len(devices)+1 non-decreasing row offsets from 0 to len(x)")
             B.check(B.lib().b200bo_multi_gpu_acq_eval(
                 specs, len(self.devices), B.as_dp(x), m,
                 off.ctypes.data_as(C.POINTER(C.c_int64)) if off is not None else None, B.as_dp(out)))
